@@ -1,0 +1,168 @@
+/*
+ * l2s_b200 -- C ABI of the B200-native (sm_100a) L2S hot path: batched disjunctive-graph evaluator and
+ * N5 local-search step for job-shop scheduling.
+ *
+ * This is the drop-in boundary.  The reference (zcaicaros/L2S) is pure Python; the calls below are what a
+ * Python binding (ctypes) needs in order to replace, with identical results:
+ *
+ *   l2s_eval_coo            <- Evaluator.forward                 env/message_passing_evl.py:161-199
+ *   l2s_load_instances      <- JsspN5.reset (instance ingest)     env/environment.py:389-390
+ *   l2s_build_initial       <- JsspN5._rules_solver               env/environment.py:203-255
+ *                              + permissibleLeftShift             env/permissible_LS.py:5-78
+ *   l2s_set_solution        <- (inject a machine order; what _rules_solver produces in opIDsOnMchs,
+ *                               env/environment.py:221,254-255)
+ *   l2s_step / l2s_step_host<- JsspN5.step                        env/environment.py:356-387
+ *                              = change_nxgraph_topology :318-354, dag2pyg :291-316, reward/incumbent
+ *                                :359-367, tabu :370-380, feasible_actions :411-423 (_gen_moves :72-81,
+ *                                nx.dag_longest_path, _get_pairs :84-105)
+ *   l2s_run                 <- the rollout loops of test_learned.py:185-189 / Greedy_baselines
+ *                              (conventional_baselines_with_long-term-mem.py:154-221) with an on-device
+ *                              policy, K steps per launch and no host round trip
+ *
+ * Conventions: plain C, no torch types.  Unless a parameter name ends in `_host`, every pointer is a DEVICE
+ * pointer owned by the caller; the library owns only the opaque handle.  Calls are asynchronous and ordered
+ * on the `cudaStream_t` passed as `void* stream` (NULL = default stream) unless stated otherwise.
+ * Every function returns L2S_OK (0) or a negative l2s_status.  Per-instance problems found on the device
+ * (illegal action, cyclic selection, ...) are reported through the `status` output array / l2s_poll_error.
+ *
+ * Node ids follow the reference: S = 0, operations 1..n row-major by (job, position), T = n+1, n = n_j*n_m;
+ * in batched tensors instance b is offset by b*(n+2).
+ */
+#ifndef L2S_B200_H_
+#define L2S_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct l2s_handle_s* l2s_handle;
+
+typedef enum {
+  L2S_OK = 0,
+  L2S_ERR_INVALID_ARG = -1,
+  L2S_ERR_CUDA = -2,
+  L2S_ERR_UNSUPPORTED_SHAPE = -3, /* n_m > 32, n+2 > 65535, or state does not fit shared memory        */
+  L2S_ERR_ILLEGAL_ACTION = -4,    /* (a0,a1) is not an adjacent pair on one machine; reference: networkx
+                                     NetworkXError from remove_edge, env/environment.py:348             */
+  L2S_ERR_BAD_GRAPH = -5,         /* cyclic selection / malformed COO (reference: evaluator runs N sweeps
+                                     and nx.dag_longest_path raises)                                    */
+  L2S_ERR_DURATION_RANGE = -6,    /* durations must be in [1, 16383] and n*max(dur) < 2^24               */
+  L2S_ERR_MACHINE_ROWS = -7,      /* every job must visit machines 1..n_m exactly once                    */
+  L2S_ERR_PAIR_OVERFLOW = -8,     /* more N5 pairs than `pmax`; recreate the handle with a larger pmax    */
+  L2S_ERR_SHORT_PATH = -9,        /* critical path of exactly two ops on one machine; the reference raises
+                                     IndexError in _get_pairs, env/environment.py:89-90                   */
+  L2S_ERR_BAD_SOLUTION = -10      /* l2s_set_solution: rows are not the operations of that machine        */
+} l2s_status;
+
+enum { L2S_REWARD_YAOXIN = 0, L2S_REWARD_CONSECUTIVE = 1 };        /* env/environment.py:359-364 */
+enum { L2S_RULE_SPT = 0, L2S_RULE_FDD_DIVIDE_MWKR = 1 };           /* env/environment.py:227-238 */
+enum { L2S_POLICY_REPLAY = 0, L2S_POLICY_RANDOM = 1, L2S_POLICY_GREEDY = 2 };
+
+const char* l2s_status_string(int status);
+int l2s_version(void);
+
+/* ---- environment handle -------------------------------------------------------------------------- */
+
+/* One handle per (rank, batch slice).  `pmax` = capacity of the per-instance N5 pair list (>= 1; 0 picks
+ * the default 32).  Allocates all device state once; no allocation happens in any later call. */
+int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* out);
+int l2s_destroy(l2s_handle h);
+
+/* Queries (host only). */
+int l2s_pmax(l2s_handle h);
+int64_t l2s_edges_mc_per_instance(l2s_handle h); /* n_m*(n_j-1) */
+int64_t l2s_itr(l2s_handle h);                   /* steps applied since the last reset (JsspN5.itr)      */
+int l2s_launch_info(l2s_handle h, int* warps_per_cta_step, int* smem_per_instance, int* warps_per_cta_run);
+
+/* Durations and 1-based machine ids, both [batch, n_j*n_m] int32 (the reference's instances[:,0], [:,1]).
+ * `instance_offset` is the global index of this slice's first instance (keys the RANDOM policy's counter
+ * RNG so that sharding a batch over ranks does not change trajectories). */
+int l2s_load_instances(l2s_handle h, const int32_t* dur, const int32_t* mch, int64_t instance_offset, void* stream);
+
+/* Install a solution: mseq[b, m, k] = node id (1..n) of the k-th operation on machine m (0-based m).
+ * Clears tabu lists, tie-break history and the step counter; does not evaluate (call l2s_step with
+ * actions == NULL and is_reset = 1). */
+int l2s_set_solution(l2s_handle h, const int32_t* mseq, void* stream);
+
+/* Build the initial solution on the device by priority dispatching with permissible left shift.
+ * Priority ties take the first tied job in job order (the reference draws np.random.choice there). */
+int l2s_build_initial(l2s_handle h, int rule, int high, void* stream);
+
+/* Copy the current machine orders out: mseq [batch, n_m, n_j] int32. */
+int l2s_get_solution(l2s_handle h, int32_t* mseq, void* stream);
+
+typedef struct {
+  /* inputs */
+  const int32_t* actions; /* [batch,2] (a0,a1); (0,0) = dummy; NULL = no move (re-evaluate only)          */
+  float high;             /* x[:,0] = dur / high            env/environment.py:312                         */
+  float fea_norm_const;   /* x[:,1:] = est|lst / const                                                     */
+  int32_t reward_type;    /* L2S_REWARD_*                                                                  */
+  int32_t is_reset;       /* 1: incumbent = current = makespan, reward = 0 (JsspN5.reset :403-405)         */
+  /* outputs (any may be NULL) */
+  float* x;               /* [batch*(n+2), 3]                                                              */
+  int64_t* edge_index_mc; /* [2, batch*n_m*(n_j-1)], ascending source per instance                         */
+  float* makespan;        /* [batch] current_objs                                                          */
+  float* incumbent;       /* [batch] incumbent_objs                                                        */
+  float* reward;          /* [batch]                                                                       */
+  uint8_t* done;          /* [batch] 1 = no feasible move ([[0,0]] in the reference)                       */
+  int32_t* pairs;         /* [batch, pmax, 2] feasible N5 pairs in critical-path order                     */
+  int32_t* npairs;        /* [batch]                                                                       */
+  int32_t* status;        /* [batch] 0 or a negative l2s_status for that instance                          */
+} l2s_step_io;
+
+/* One environment step for the whole slice, one kernel launch: swap, re-evaluate, features, machine edges,
+ * reward/incumbent/tabu update, critical path, N5 move set. */
+int l2s_step(l2s_handle h, const l2s_step_io* io, void* stream);
+
+/* Same step driven from HOST memory: copies `actions_host` ([batch,2] int32, may be NULL) to the device,
+ * runs l2s_step with the device outputs in `io` (io->actions is ignored), copies the move sets back and
+ * synchronises the stream.  Host outputs may be NULL.  pairs_host is [batch,pmax,2] int32. */
+int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_host, int32_t* pairs_host,
+                  int32_t* npairs_host, uint8_t* done_host, float* reward_host, float* makespan_host,
+                  int32_t* status_host, void* stream);
+
+/* Pinned host buffers that l2s_step_host fills (zero-copy views for a binding; any out-pointer may be
+ * NULL): pairs [batch,pmax,2], npairs/status [batch] int32, reward/makespan/incumbent [batch] float,
+ * done [batch] uint8, and the pinned action staging buffer [batch,2] int32 (write actions there and pass
+ * the same pointer as actions_host to skip a host copy). */
+int l2s_host_buffers(l2s_handle h, int32_t** pairs, int32_t** npairs, int32_t** status, float** reward,
+                     float** makespan, float** incumbent, uint8_t** done, int32_t** actions);
+
+/* K fused steps in ONE launch with an on-device policy; the search state never leaves shared memory.
+ *   REPLAY: tape [batch, K, 2] int32 actions.
+ *   RANDOM: uniformly among the feasible pairs, index = mix64(seed, global instance, step) (see oracle).
+ *   GREEDY: best neighbour by makespan, first minimum in move-list order, always moves.
+ * taken (nullable) [batch, K, 2] receives the actions applied; incumbent_log (nullable)
+ * [n_log, batch] float receives incumbents after log_steps_host[i] steps (ascending, 1-based counts). */
+int l2s_run(l2s_handle h, int policy, int K, const int32_t* tape, uint64_t seed, int32_t* taken,
+            const int32_t* log_steps_host, int n_log, float* incumbent_log, void* stream);
+
+/* Test introspection (re-evaluates the current solution, mutates nothing): any pointer may be NULL.
+ * est/lst [batch, n+2] int32 (both or neither), path [batch, n] int32 + path_len [batch] (both or neither),
+ * tabu [batch,2], jobfirst [batch, n+2] uint8, makespan/incumbent [batch] float. */
+int l2s_export_state(l2s_handle h, int32_t* est, int32_t* lst, int32_t* path, int32_t* path_len,
+                     int32_t* tabu, uint8_t* jobfirst, float* makespan, float* incumbent, void* stream);
+
+/* Synchronises `stream` and returns the first device-side error recorded since the last poll
+ * (0 if none); *instance_out (nullable) receives the slice-local instance index. */
+int l2s_poll_error(l2s_handle h, int* instance_out, void* stream);
+
+/* ---- stateless evaluator (drop-in for Evaluator.forward) ------------------------------------------- */
+
+/* Bytes of scratch the caller must provide for a batch of `batch` graphs. */
+int64_t l2s_eval_coo_workspace_bytes(int n_j, int n_m, int64_t batch);
+
+/* edge_index [2,E] int64 COO in any order (conjunctive + machine arcs of `batch` complete selections),
+ * duration [batch*(n+2)] int32 or int64 (`duration_is_i64`), outputs est/lst [batch*(n+2)] and
+ * makespan [batch] as float32 (integer valued, like the reference).  status_flag: one int32 on the
+ * device, set to a negative l2s_status if the input is not a batch of acyclic JSSP selections. */
+int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duration, int duration_is_i64,
+                 int n_j, int n_m, int64_t batch, float* est, float* lst, float* makespan,
+                 void* workspace, int64_t workspace_bytes, int32_t* status_flag, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L2S_B200_H_ */

@@ -1,0 +1,476 @@
+// l2s_b200 C ABI (include/l2s_b200.h): handle management and kernel launches.  No torch, no Python: a plain
+// CUDA shared library (libl2s_b200.so) that the Python drop-in binds with ctypes.
+#include "../../include/l2s_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "l2s_kernels.cuh"
+
+using namespace l2s;
+
+namespace {
+
+constexpr size_t kSmemPerSm = 233472;      // 228 KB
+constexpr size_t kSmemPerCtaMax = 232448;  // 227 KB opt-in
+constexpr size_t kSmemCtaReserve = 1024;
+
+inline int ru(long long x, int a) { return (int)((x + a - 1) / a * a); }
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      fprintf(stderr, "l2s_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return L2S_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+Layout make_layout(int n_j, int n_m) {
+  Layout L;
+  memset(&L, 0, sizeof(L));
+  L.n_j = n_j;
+  L.n_m = n_m;
+  L.n = n_j * n_m;
+  L.n1 = L.n + 2;
+  L.n1p = ru(L.n1, 4);
+  L.seq_stride = ru(L.n, 8);
+  L.node_stride = ru(L.n1, 8);
+  L.mch_stride = ru(L.n, 16);
+  L.jf_words = ru((L.n1 + 31) / 32, 4);
+  L.e_mc = n_m * (n_j - 1);
+  int off = 0;
+  L.off_tq = off;   off += 2 * L.n1p * 4;
+  L.off_seq = off;  off += L.seq_stride * 2;
+  L.off_durw = off; off += L.node_stride * 2;
+  L.off_crit = off; off += L.node_stride * 2;
+  L.off_mch = off;  off += L.mch_stride;
+  L.off_jf = off;   off += L.jf_words * 4;
+  L.off_misc = off; off += kMiscInts * 4;
+  L.bytes = ru(off, 16);
+  return L;
+}
+
+// warps (= instances) per CTA that maximise resident warps per SM; 0 if one instance does not fit
+int pick_warps(size_t bytes_per_inst) {
+  int best = 0, best_w = 0;
+  const int cand[] = {1, 2, 4, 8, 16};
+  for (int w : cand) {
+    const size_t need = (size_t)w * bytes_per_inst;
+    if (need > kSmemPerCtaMax) continue;
+    long long ctas = (long long)(kSmemPerSm / (need + kSmemCtaReserve));
+    if (ctas > 32) ctas = 32;
+    long long warps = ctas * w;
+    if (warps > 64) warps = 64;
+    if (warps > best) { best = (int)warps; best_w = w; }
+  }
+  return best_w;
+}
+
+}  // namespace
+
+struct l2s_handle_s {
+  int device;
+  int B, pmax;
+  Layout L;
+  State st;
+  long long inst_off;
+  long long itr;
+  int warps_step, warps_run, warps_init;
+  size_t run_stride;
+  InitLayout IL;
+  // staging for the host-driven step
+  int32_t* d_actions;
+  int32_t* h_actions;     // pinned
+  unsigned char* d_pack;
+  unsigned char* h_pack;  // pinned
+  size_t pack_bytes;
+  size_t off_npairs, off_status, off_reward, off_ms, off_inc, off_done, off_pairs;
+};
+
+extern "C" {
+
+const char* l2s_status_string(int s) {
+  switch (s) {
+    case L2S_OK: return "ok";
+    case L2S_ERR_INVALID_ARG: return "invalid argument";
+    case L2S_ERR_CUDA: return "CUDA error";
+    case L2S_ERR_UNSUPPORTED_SHAPE: return "unsupported shape (n_m > 32, n+2 > 65535 or state exceeds shared memory)";
+    case L2S_ERR_ILLEGAL_ACTION: return "illegal action: not an adjacent pair on one machine";
+    case L2S_ERR_BAD_GRAPH: return "cyclic or malformed disjunctive graph";
+    case L2S_ERR_DURATION_RANGE: return "duration out of range [1,16383] or total duration >= 2^24";
+    case L2S_ERR_MACHINE_ROWS: return "every job must visit machines 1..n_m exactly once";
+    case L2S_ERR_PAIR_OVERFLOW: return "more N5 pairs than pmax";
+    case L2S_ERR_SHORT_PATH: return "critical path of two operations on one machine (reference raises IndexError)";
+    case L2S_ERR_BAD_SOLUTION: return "machine order rows are not the operations of that machine";
+    default: return "unknown status";
+  }
+}
+
+int l2s_version(void) { return 100; }
+
+int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* out) {
+  if (!out || n_j < 2 || n_m < 1 || batch < 1 || pmax < 0) return L2S_ERR_INVALID_ARG;
+  if (pmax == 0) pmax = 32;
+  if (n_m > 32 || (long long)n_j * n_m + 2 > 65535) return L2S_ERR_UNSUPPORTED_SHAPE;
+  CU(cudaSetDevice(device));
+  l2s_handle h = (l2s_handle)calloc(1, sizeof(l2s_handle_s));
+  if (!h) return L2S_ERR_INVALID_ARG;
+  h->device = device;
+  h->B = batch;
+  h->pmax = pmax;
+  h->L = make_layout(n_j, n_m);
+  const Layout& L = h->L;
+  h->run_stride = ru((long long)L.bytes + (long long)pmax * 4, 16);
+  // initial-solution builder layout
+  {
+    InitLayout& I = h->IL;
+    int off = 0;
+    I.off_starts = off; off += ru((long long)L.n * 4, 16);
+    I.off_ops = off;    off += ru((long long)L.n * 2, 16);
+    I.off_cnt = off;    off += ru((long long)n_m * 4, 16);
+    I.off_nxt = off;    off += ru((long long)n_j * 4, 16);
+    I.off_rdy = off;    off += ru((long long)n_j * 4, 16);
+    I.off_work = off;   off += ru((long long)n_j * 4, 16);
+    I.off_tot = off;    off += ru((long long)n_j * 4, 16);
+    I.off_pri = off;    off += ru((long long)n_j * 8, 16);
+    I.bytes = off;
+  }
+  h->warps_step = pick_warps(L.bytes);
+  h->warps_run = pick_warps(h->run_stride);
+  h->warps_init = pick_warps(h->IL.bytes);
+  if (!h->warps_step || !h->warps_run || !h->warps_init) { free(h); return L2S_ERR_UNSUPPORTED_SHAPE; }
+  CU(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
+  CU(cudaFuncSetAttribute(run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
+  CU(cudaFuncSetAttribute(build_initial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
+  const size_t B = batch;
+  State& st = h->st;
+  CU(cudaMalloc(&st.durw, B * L.node_stride * 2));
+  CU(cudaMalloc(&st.mch, B * L.mch_stride));
+  CU(cudaMalloc(&st.seq, B * L.seq_stride * 2));
+  CU(cudaMalloc(&st.jf, B * L.jf_words * 4));
+  CU(cudaMalloc(&st.tabu, B * 8));
+  CU(cudaMalloc(&st.cur, B * 4));
+  CU(cudaMalloc(&st.inc, B * 4));
+  CU(cudaMalloc(&st.err, 4));
+  CU(cudaMemset(st.durw, 0, B * L.node_stride * 2));
+  CU(cudaMemset(st.mch, 0, B * L.mch_stride));
+  CU(cudaMemset(st.seq, 0, B * L.seq_stride * 2));
+  CU(cudaMemset(st.jf, 0, B * L.jf_words * 4));
+  CU(cudaMemset(st.tabu, 0, B * 8));
+  CU(cudaMemset(st.cur, 0, B * 4));
+  CU(cudaMemset(st.inc, 0, B * 4));
+  CU(cudaMemset(st.err, 0, 4));
+  // host-step staging: one packed result block so that a step needs a single D2H copy
+  size_t off = 0;
+  h->off_npairs = off; off += ru(B * 4, 16);
+  h->off_status = off; off += ru(B * 4, 16);
+  h->off_reward = off; off += ru(B * 4, 16);
+  h->off_ms = off;     off += ru(B * 4, 16);
+  h->off_inc = off;    off += ru(B * 4, 16);
+  h->off_done = off;   off += ru(B, 16);
+  h->off_pairs = off;  off += ru(B * pmax * 8, 16);
+  h->pack_bytes = off;
+  CU(cudaMalloc(&h->d_pack, h->pack_bytes));
+  CU(cudaMemset(h->d_pack, 0, h->pack_bytes));
+  CU(cudaMallocHost(&h->h_pack, h->pack_bytes));
+  memset(h->h_pack, 0, h->pack_bytes);
+  CU(cudaMalloc(&h->d_actions, B * 8));
+  CU(cudaMallocHost(&h->h_actions, B * 8));
+  *out = h;
+  return L2S_OK;
+}
+
+int l2s_destroy(l2s_handle h) {
+  if (!h) return L2S_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->st.durw); cudaFree(h->st.mch); cudaFree(h->st.seq); cudaFree(h->st.jf);
+  cudaFree(h->st.tabu); cudaFree(h->st.cur); cudaFree(h->st.inc); cudaFree(h->st.err);
+  cudaFree(h->d_pack); cudaFreeHost(h->h_pack); cudaFree(h->d_actions); cudaFreeHost(h->h_actions);
+  free(h);
+  return L2S_OK;
+}
+
+int l2s_pmax(l2s_handle h) { return h ? h->pmax : L2S_ERR_INVALID_ARG; }
+int64_t l2s_edges_mc_per_instance(l2s_handle h) { return h ? h->L.e_mc : L2S_ERR_INVALID_ARG; }
+int64_t l2s_itr(l2s_handle h) { return h ? h->itr : L2S_ERR_INVALID_ARG; }
+
+int l2s_launch_info(l2s_handle h, int* warps_per_cta_step, int* smem_per_instance, int* warps_per_cta_run) {
+  if (!h) return L2S_ERR_INVALID_ARG;
+  if (warps_per_cta_step) *warps_per_cta_step = h->warps_step;
+  if (smem_per_instance) *smem_per_instance = h->L.bytes;
+  if (warps_per_cta_run) *warps_per_cta_run = h->warps_run;
+  return L2S_OK;
+}
+
+static inline dim3 warp_grid(int B, int threads) { return dim3((unsigned)(((long long)B * 32 + threads - 1) / threads)); }
+
+int l2s_load_instances(l2s_handle h, const int32_t* dur, const int32_t* mch, int64_t instance_offset, void* stream) {
+  if (!h || !dur || !mch) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  h->inst_off = instance_offset;
+  load_kernel<<<warp_grid(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->L, h->st, h->B, dur, mch);
+  CU(cudaGetLastError());
+  return L2S_OK;
+}
+
+int l2s_set_solution(l2s_handle h, const int32_t* mseq, void* stream) {
+  if (!h || !mseq) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  h->itr = 0;
+  set_solution_kernel<<<warp_grid(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->L, h->st, h->B, mseq);
+  CU(cudaGetLastError());
+  return L2S_OK;
+}
+
+int l2s_get_solution(l2s_handle h, int32_t* mseq, void* stream) {
+  if (!h || !mseq) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  get_solution_kernel<<<warp_grid(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->L, h->st, h->B, mseq);
+  CU(cudaGetLastError());
+  return L2S_OK;
+}
+
+int l2s_build_initial(l2s_handle h, int rule, int high, void* stream) {
+  if (!h || (rule != L2S_RULE_SPT && rule != L2S_RULE_FDD_DIVIDE_MWKR)) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  h->itr = 0;
+  const int W = h->warps_init;
+  build_initial_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * h->IL.bytes, (cudaStream_t)stream>>>(
+      h->L, h->IL, h->st, h->B, rule, high);
+  CU(cudaGetLastError());
+  return L2S_OK;
+}
+
+static int launch_step(l2s_handle h, const StepArgs& a, void* stream) {
+  const int W = h->warps_step;
+  step_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * h->L.bytes, (cudaStream_t)stream>>>(a);
+  CU(cudaGetLastError());
+  return L2S_OK;
+}
+
+static StepArgs step_args(l2s_handle h, const l2s_step_io* io) {
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.L = h->L;
+  a.st = h->st;
+  a.B = h->B;
+  a.pmax = h->pmax;
+  if (io) {
+    a.actions = io->actions;
+    a.high = io->high;
+    a.fea = io->fea_norm_const;
+    a.reward_type = io->reward_type;
+    a.is_reset = io->is_reset;
+    a.x = io->x;
+    a.emc = io->edge_index_mc;
+    a.makespan = io->makespan;
+    a.incumbent = io->incumbent;
+    a.reward = io->reward;
+    a.done = io->done;
+    a.pairs = io->pairs;
+    a.npairs = io->npairs;
+    a.status = io->status;
+  }
+  return a;
+}
+
+int l2s_step(l2s_handle h, const l2s_step_io* io, void* stream) {
+  if (!h || !io) return L2S_ERR_INVALID_ARG;
+  if (io->reward_type != L2S_REWARD_YAOXIN && io->reward_type != L2S_REWARD_CONSECUTIVE) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  StepArgs a = step_args(h, io);
+  int r = launch_step(h, a, stream);
+  if (r == L2S_OK && !io->is_reset && a.actions) h->itr += 1;
+  return r;
+}
+
+int l2s_host_buffers(l2s_handle h, int32_t** pairs, int32_t** npairs, int32_t** status, float** reward,
+                     float** makespan, float** incumbent, uint8_t** done, int32_t** actions) {
+  if (!h) return L2S_ERR_INVALID_ARG;
+  if (pairs) *pairs = (int32_t*)(h->h_pack + h->off_pairs);
+  if (npairs) *npairs = (int32_t*)(h->h_pack + h->off_npairs);
+  if (status) *status = (int32_t*)(h->h_pack + h->off_status);
+  if (reward) *reward = (float*)(h->h_pack + h->off_reward);
+  if (makespan) *makespan = (float*)(h->h_pack + h->off_ms);
+  if (incumbent) *incumbent = (float*)(h->h_pack + h->off_inc);
+  if (done) *done = (uint8_t*)(h->h_pack + h->off_done);
+  if (actions) *actions = h->h_actions;
+  return L2S_OK;
+}
+
+int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_host, int32_t* pairs_host,
+                  int32_t* npairs_host, uint8_t* done_host, float* reward_host, float* makespan_host,
+                  int32_t* status_host, void* stream) {
+  if (!h || !io) return L2S_ERR_INVALID_ARG;
+  if (io->reward_type != L2S_REWARD_YAOXIN && io->reward_type != L2S_REWARD_CONSECUTIVE) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t B = h->B;
+  StepArgs a = step_args(h, io);
+  a.actions = nullptr;
+  if (actions_host) {
+    if (actions_host != h->h_actions) memcpy(h->h_actions, actions_host, B * 8);
+    CU(cudaMemcpyAsync(h->d_actions, h->h_actions, B * 8, cudaMemcpyHostToDevice, s));
+    a.actions = h->d_actions;
+  }
+  // results the host needs go to the packed block; per-instance scalars are mirrored there by the kernel
+  a.pairs = (int32_t*)(h->d_pack + h->off_pairs);
+  a.npairs = (int32_t*)(h->d_pack + h->off_npairs);
+  a.status = (int32_t*)(h->d_pack + h->off_status);
+  a.reward2 = (float*)(h->d_pack + h->off_reward);
+  a.makespan2 = (float*)(h->d_pack + h->off_ms);
+  a.incumbent2 = (float*)(h->d_pack + h->off_inc);
+  a.done2 = (uint8_t*)(h->d_pack + h->off_done);
+  int r = launch_step(h, a, stream);
+  if (r != L2S_OK) return r;
+  if (!io->is_reset && a.actions) h->itr += 1;
+  CU(cudaMemcpyAsync(h->h_pack, h->d_pack, h->pack_bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (pairs_host) memcpy(pairs_host, h->h_pack + h->off_pairs, B * h->pmax * 8);
+  if (npairs_host) memcpy(npairs_host, h->h_pack + h->off_npairs, B * 4);
+  if (status_host) memcpy(status_host, h->h_pack + h->off_status, B * 4);
+  if (reward_host) memcpy(reward_host, h->h_pack + h->off_reward, B * 4);
+  if (makespan_host) memcpy(makespan_host, h->h_pack + h->off_ms, B * 4);
+  if (done_host) memcpy(done_host, h->h_pack + h->off_done, B);
+  // device copies requested by the caller in io (rare: the host path normally leaves these NULL)
+  if (io->pairs) CU(cudaMemcpyAsync(io->pairs, a.pairs, B * h->pmax * 8, cudaMemcpyDeviceToDevice, s));
+  if (io->npairs) CU(cudaMemcpyAsync(io->npairs, a.npairs, B * 4, cudaMemcpyDeviceToDevice, s));
+  if (io->status) CU(cudaMemcpyAsync(io->status, a.status, B * 4, cudaMemcpyDeviceToDevice, s));
+  return L2S_OK;
+}
+
+int l2s_run(l2s_handle h, int policy, int K, const int32_t* tape, uint64_t seed, int32_t* taken,
+            const int32_t* log_steps_host, int n_log, float* incumbent_log, void* stream) {
+  if (!h || K < 0 || policy < 0 || policy > 2 || n_log < 0 || n_log > kMaxLog) return L2S_ERR_INVALID_ARG;
+  if (policy == L2S_POLICY_REPLAY && !tape) return L2S_ERR_INVALID_ARG;
+  if (n_log > 0 && (!log_steps_host || !incumbent_log)) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  RunArgs a;
+  memset(&a, 0, sizeof(a));
+  a.L = h->L;
+  a.st = h->st;
+  a.B = h->B;
+  a.policy = policy;
+  a.K = K;
+  a.tape = tape;
+  a.seed = seed;
+  a.inst_off = h->inst_off;
+  a.itr0 = h->itr;
+  a.taken = taken;
+  a.n_log = n_log;
+  for (int i = 0; i < n_log; ++i) {
+    if (i && log_steps_host[i] <= log_steps_host[i - 1]) return L2S_ERR_INVALID_ARG;
+    a.log_steps[i] = log_steps_host[i];
+  }
+  a.inc_log = incumbent_log;
+  a.pmax = h->pmax;
+  a.off_plist = h->L.bytes;
+  a.stride = (int)h->run_stride;
+  const int W = h->warps_run;
+  run_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * h->run_stride, (cudaStream_t)stream>>>(a);
+  CU(cudaGetLastError());
+  h->itr += K;
+  return L2S_OK;
+}
+
+int l2s_export_state(l2s_handle h, int32_t* est, int32_t* lst, int32_t* path, int32_t* path_len, int32_t* tabu,
+                     uint8_t* jobfirst, float* makespan, float* incumbent, void* stream) {
+  if (!h) return L2S_ERR_INVALID_ARG;
+  if ((est == nullptr) != (lst == nullptr) || (path == nullptr) != (path_len == nullptr)) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (est || path) {
+    StepArgs a = step_args(h, nullptr);
+    a.export_only = 1;
+    a.high = 1.f;
+    a.fea = 1.f;
+    a.ex_est = est;
+    a.ex_lst = lst;
+    a.ex_path = path;
+    a.ex_path_len = path_len;
+    int r = launch_step(h, a, stream);
+    if (r != L2S_OK) return r;
+  }
+  if (tabu) CU(cudaMemcpyAsync(tabu, h->st.tabu, (size_t)h->B * 8, cudaMemcpyDeviceToDevice, s));
+  if (jobfirst || makespan || incumbent) {
+    export_misc_kernel<<<warp_grid(h->B, 128), 128, 0, s>>>(h->L, h->st, h->B, jobfirst, makespan, incumbent);
+    CU(cudaGetLastError());
+  }
+  return L2S_OK;
+}
+
+int l2s_poll_error(l2s_handle h, int* instance_out, void* stream) {
+  if (!h) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  int word = 0;
+  CU(cudaMemcpyAsync(&word, h->st.err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  if (!word) return L2S_OK;
+  CU(cudaMemsetAsync(h->st.err, 0, 4, (cudaStream_t)stream));
+  if (instance_out) *instance_out = word & 0xffffff;
+  return -(int)(((unsigned)word) >> 24);
+}
+
+// ---- stateless COO evaluator -------------------------------------------------------------------------
+
+int64_t l2s_eval_coo_workspace_bytes(int n_j, int n_m, int64_t batch) {
+  if (n_j < 1 || n_m < 1 || batch < 1) return L2S_ERR_INVALID_ARG;
+  const long long node_stride = ru((long long)n_j * n_m + 2, 8);
+  return 2 * batch * node_stride * 2 + 16;
+}
+
+int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duration, int duration_is_i64, int n_j,
+                 int n_m, int64_t batch, float* est, float* lst, float* makespan, void* workspace,
+                 int64_t workspace_bytes, int32_t* status_flag, int device, void* stream) {
+  if (!edge_index || !duration || !est || !lst || !makespan || !workspace || !status_flag || batch < 1 ||
+      n_j < 1 || n_m < 1 || n_edges < 0)
+    return L2S_ERR_INVALID_ARG;
+  const long long n = (long long)n_j * n_m;
+  if (n + 2 > 65535) return L2S_ERR_UNSUPPORTED_SHAPE;
+  if (workspace_bytes < l2s_eval_coo_workspace_bytes(n_j, n_m, batch)) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CooEvalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_j = n_j; a.n_m = n_m; a.n = (int)n; a.n1 = (int)n + 2; a.n1p = ru(a.n1, 4); a.node_stride = ru(a.n1, 8);
+  a.B = batch;
+  a.duration = duration;
+  a.dur_i64 = duration_is_i64;
+  const size_t links = (size_t)batch * a.node_stride * 2;
+  a.ws.msucc = (uint16_t*)workspace;
+  a.ws.mpred = (uint16_t*)((char*)workspace + links);
+  a.ws.conj_count = (unsigned long long*)((char*)workspace + 2 * links);
+  a.ws.flag = status_flag;
+  a.est = est; a.lst = lst; a.ms = makespan;
+  a.expect_conj = batch * ((long long)n_j * (n_m + 1));
+  int off = 0;
+  a.off_tq = off;    off += 2 * a.n1p * 4;
+  a.off_durw = off;  off += a.node_stride * 2;
+  a.off_succ = off;  off += a.node_stride * 2;
+  a.off_pred = off;  off += a.node_stride * 2;
+  a.off_heads = off; off += 128;
+  a.bytes = ru(off, 16);
+  const int W = pick_warps(a.bytes);
+  if (!W) return L2S_ERR_UNSUPPORTED_SHAPE;
+  static bool attr_set[64] = {false};
+  if (device >= 0 && device < 64 && !attr_set[device]) {
+    CU(cudaFuncSetAttribute(coo_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
+    attr_set[device] = true;
+  }
+  CU(cudaMemsetAsync(workspace, 0, 2 * links + 16, s));
+  CU(cudaMemsetAsync(status_flag, 0, 4, s));
+  if (n_edges > 0) {
+    const long long blocks = (n_edges + 255) / 256;
+    coo_ingest_kernel<<<(unsigned)blocks, 256, 0, s>>>((const long long*)edge_index, n_edges, n_j, n_m, batch,
+                                                       a.node_stride, a.ws);
+    CU(cudaGetLastError());
+  }
+  coo_eval_kernel<<<(unsigned)((batch + W - 1) / W), W * 32, (size_t)W * a.bytes, s>>>(a);
+  CU(cudaGetLastError());
+  return L2S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,761 @@
+// l2s_b200 kernels (sm_100a): environment step, fused K-step run, setup, initial-solution builder and the
+// stateless COO evaluator.  See l2s_device.cuh for the execution model.
+#pragma once
+#include "l2s_device.cuh"
+
+namespace l2s {
+
+// ------------------------------------------------------------------------------------------------------
+// setup kernels (one warp per instance; not on the hot path)
+// ------------------------------------------------------------------------------------------------------
+
+// int32 durations / machine ids -> packed node words + byte machine ids, with input validation.
+__global__ void load_kernel(Layout L, State st, int B, const int32_t* __restrict__ dur,
+                            const int32_t* __restrict__ mch) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  int bad = 0;
+  long long sum = 0;
+  for (int v = lane; v < L.node_stride; v += 32) {
+    int word = 0;
+    if (v >= 1 && v <= L.n) {
+      const int d = dur[(size_t)b * L.n + v - 1];
+      if (d < 1 || d > kDurMask) bad |= 1;
+      const int pos = (v - 1) % L.n_m;
+      word = (d & kDurMask) | (pos == 0 ? kFirstFlag : 0) | (pos == L.n_m - 1 ? kLastFlag : 0);
+      sum += d;
+    }
+    st.durw[(size_t)b * L.node_stride + v] = (uint16_t)word;
+  }
+  for (int i = lane; i < L.mch_stride; i += 32) {
+    int mc = 0;
+    if (i < L.n) {
+      mc = mch[(size_t)b * L.n + i];
+      if (mc < 1 || mc > L.n_m) { bad |= 2; mc = 1; }
+    }
+    st.mch[(size_t)b * L.mch_stride + i] = (uint8_t)mc;
+  }
+  const unsigned full = L.n_m == 32 ? 0xffffffffu : ((1u << L.n_m) - 1u);
+  for (int j = lane; j < L.n_j; j += 32) {
+    unsigned mask = 0;
+    for (int k = 0; k < L.n_m; ++k) mask |= 1u << ((mch[(size_t)b * L.n + j * L.n_m + k] - 1) & 31);
+    if (mask != full) bad |= 2;
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+  if (sum >= (1ll << 24)) bad |= 1;
+  bad = __reduce_or_sync(kFull, bad);
+  if (bad && lane == 0) record_error(st.err, (bad & 2) ? -7 : -6, b);
+}
+
+__device__ __forceinline__ void reset_dynamic(const Layout& L, const State& st, int b, int lane) {
+  for (int i = lane; i < L.jf_words; i += 32) st.jf[(size_t)b * L.jf_words + i] = 0;
+  if (lane == 0) {
+    st.tabu[2 * b] = 0;
+    st.tabu[2 * b + 1] = 0;
+    st.cur[b] = 0;
+    st.inc[b] = 0;
+  }
+}
+
+// mseq [B, n_m, n_j] int32 node ids -> uint16 machine orders; validates rows.
+__global__ void set_solution_kernel(Layout L, State st, int B, const int32_t* __restrict__ mseq) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  uint32_t* seen = st.jf + (size_t)b * L.jf_words;
+  for (int i = lane; i < L.jf_words; i += 32) seen[i] = 0;
+  __syncwarp();
+  int bad = 0;
+  for (int m = 0; m < L.n_m; ++m) {
+    for (int k = lane; k < L.n_j; k += 32) {
+      const int idx = m * L.n_j + k;
+      int v = mseq[(size_t)b * L.n + idx];
+      if (v < 1 || v > L.n || (int)st.mch[(size_t)b * L.mch_stride + v - 1] - 1 != m) {
+        bad = 1;
+        v = 1;
+      } else {
+        const unsigned old = atomicOr(&seen[v >> 5], 1u << (v & 31));
+        if (old & (1u << (v & 31))) bad = 1;
+      }
+      st.seq[(size_t)b * L.seq_stride + idx] = (uint16_t)v;
+    }
+  }
+  for (int i = L.n + lane; i < L.seq_stride; i += 32) st.seq[(size_t)b * L.seq_stride + i] = 0;
+  __syncwarp();
+  reset_dynamic(L, st, b, lane);
+  bad = __reduce_or_sync(kFull, bad);
+  if (bad && lane == 0) record_error(st.err, -10, b);
+}
+
+__global__ void get_solution_kernel(Layout L, State st, int B, int32_t* __restrict__ mseq) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  for (int i = lane; i < L.n; i += 32) mseq[(size_t)b * L.n + i] = st.seq[(size_t)b * L.seq_stride + i];
+}
+
+__global__ void export_misc_kernel(Layout L, State st, int B, uint8_t* jobfirst, float* makespan, float* incumbent) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  if (jobfirst)
+    for (int v = lane; v < L.n1; v += 32)
+      jobfirst[(size_t)b * L.n1 + v] = (st.jf[(size_t)b * L.jf_words + (v >> 5)] >> (v & 31)) & 1u;
+  if (lane == 0) {
+    if (makespan) makespan[b] = (float)st.cur[b];
+    if (incumbent) incumbent[b] = (float)st.inc[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Initial solution: priority dispatching with permissible left shift.
+// JsspN5._rules_solver (env/environment.py:203-255) + permissibleLeftShift (env/permissible_LS.py:5-78).
+// One warp per instance; the machine gantt rows live in shared memory.  Priorities change only for the
+// job just dispatched, so they are cached (one IEEE double division per dispatched operation).
+// Shared memory per instance: starts int32[n], ops uint16[n], cnt int32[n_m], nxt/jobrdy/done int32[n_j]x3,
+// pri double[n_j].
+// ------------------------------------------------------------------------------------------------------
+struct InitLayout {
+  int off_starts, off_ops, off_cnt, off_nxt, off_rdy, off_work, off_tot, off_pri, bytes;
+};
+
+__global__ void build_initial_kernel(Layout L, InitLayout IL, State st, int B, int rule, int high) {
+  extern __shared__ __align__(16) unsigned char smem_init[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * (blockDim.x >> 5) + w;
+  if (b >= B) return;
+  unsigned char* base = smem_init + (size_t)w * IL.bytes;
+  int32_t* starts = reinterpret_cast<int32_t*>(base + IL.off_starts);   // [n_m][n_j]
+  uint16_t* ops = reinterpret_cast<uint16_t*>(base + IL.off_ops);       // [n_m][n_j] node ids (1-based)
+  int32_t* cnt = reinterpret_cast<int32_t*>(base + IL.off_cnt);         // ops placed per machine
+  int32_t* nxt = reinterpret_cast<int32_t*>(base + IL.off_nxt);         // next position per job
+  int32_t* rdy = reinterpret_cast<int32_t*>(base + IL.off_rdy);         // completion of the job's last placed op
+  int32_t* work = reinterpret_cast<int32_t*>(base + IL.off_work);       // remaining work per job
+  int32_t* total = reinterpret_cast<int32_t*>(base + IL.off_tot);       // total work per job
+  double* pri = reinterpret_cast<double*>(base + IL.off_pri);
+  const uint16_t* durw = st.durw + (size_t)b * L.node_stride;
+  const uint8_t* mch = st.mch + (size_t)b * L.mch_stride;
+  const int n_j = L.n_j, n_m = L.n_m;
+  const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+
+  for (int m = lane; m < n_m; m += 32) cnt[m] = 0;
+  for (int j = lane; j < n_j; j += 32) {
+    int tot = 0;
+    for (int k = 0; k < n_m; ++k) tot += durw[j * n_m + k + 1] & kDurMask;
+    nxt[j] = 0;
+    rdy[j] = 0;
+    work[j] = tot;
+    total[j] = tot;
+    const int d0 = durw[j * n_m + 1] & kDurMask;
+    // fdd/mwkr: cumulative duration up to and including the candidate / remaining work (:234-236)
+    pri[j] = rule == 0 ? (double)d0 : __ddiv_rn((double)d0, (double)tot);
+  }
+  __syncwarp();
+  for (int it = 0; it < L.n; ++it) {
+    // argmin over jobs, first minimum in job order (reference: np.random.choice among ties, :237)
+    double best = kInf;
+    int bj = 0x7fffffff;
+    for (int j = lane; j < n_j; j += 32) {
+      const double p = pri[j];
+      if (p < best) { best = p; bj = j; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const double ob = __shfl_xor_sync(kFull, best, o);
+      const int oj = __shfl_xor_sync(kFull, bj, o);
+      if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+    }
+    const int j = bj;
+    const int kpos = nxt[j];
+    const int v = j * n_m + kpos + 1;           // node id
+    const int d = durw[v] & kDurMask;
+    const int m = (int)mch[v - 1] - 1;
+    int32_t* rs = starts + m * n_j;
+    uint16_t* ro = ops + m * n_j;
+    const int c = cnt[m];
+    const int job_rdy = rdy[j];
+    const int mch_rdy = c ? rs[c - 1] + (durw[ro[c - 1]] & kDurMask) : 0;
+    // first placed op that starts after job_rdy (rows are sorted by start time)
+    int p0 = c;
+    for (int k0 = 0; k0 < c; k0 += 32) {
+      const int k = k0 + lane;
+      const unsigned hit = __ballot_sync(kFull, k < c && rs[k] > job_rdy);
+      if (hit) { p0 = k0 + __ffs(hit) - 1; break; }
+    }
+    int ins = -1, start_a = 0;
+    if (p0 < c) {
+      // end of the op before the first candidate slot; for p0 == 0 the reference reads index -1, i.e. the
+      // unfilled row tail: -high + dur[flat index n - n_j] (env/permissible_LS.py:41)
+      const int before = p0 > 0 ? rs[p0 - 1] + (durw[ro[p0 - 1]] & kDurMask)
+                                : -high + (durw[L.n - n_j + 1] & kDurMask);
+      for (int k0 = p0; k0 < c; k0 += 32) {
+        const int k = k0 + lane;
+        bool fits = false;
+        int open = 0;
+        if (k < c) {
+          open = (k == p0) ? max(job_rdy, before) : rs[k - 1] + (durw[ro[k - 1]] & kDurMask);
+          fits = d <= rs[k] - open;
+        }
+        const unsigned hit = __ballot_sync(kFull, fits);
+        if (hit) {
+          const int src = __ffs(hit) - 1;
+          ins = k0 + src;
+          start_a = __shfl_sync(kFull, open, src);
+          break;
+        }
+      }
+    }
+    __syncwarp();
+    if (ins >= 0) {
+      // shift [ins, c) one slot to the right, back to front in chunks so reads precede overwrites
+      for (int hi = c; hi > ins; hi -= 32) {
+        const int k = hi - 1 - lane;           // source index
+        int sv = 0, ov = 0;
+        const bool act = k >= ins;
+        if (act) { sv = rs[k]; ov = ro[k]; }
+        __syncwarp();
+        if (act) { rs[k + 1] = sv; ro[k + 1] = (uint16_t)ov; }
+        __syncwarp();
+      }
+      if (lane == 0) { rs[ins] = start_a; ro[ins] = (uint16_t)v; }
+    } else {
+      start_a = max(job_rdy, mch_rdy);
+      if (lane == 0) { rs[c] = start_a; ro[c] = (uint16_t)v; }
+    }
+    if (lane == 0) {
+      cnt[m] = c + 1;
+      rdy[j] = start_a + d;
+      const int wk = work[j] - d;
+      work[j] = wk;
+      nxt[j] = kpos + 1;
+      if (kpos + 1 < n_m) {
+        const int dn = durw[v + 1] & kDurMask;
+        // cum(candidate) = work done so far + dur(candidate)
+        pri[j] = rule == 0 ? (double)dn : __ddiv_rn((double)(total[j] - wk + dn), (double)wk);
+      } else {
+        pri[j] = kInf;
+      }
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < L.seq_stride; i += 32) st.seq[(size_t)b * L.seq_stride + i] = i < L.n ? ops[i] : 0;
+  reset_dynamic(L, st, b, lane);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The environment step: JsspN5.step (env/environment.py:356-387), one launch for the whole slice.
+// ------------------------------------------------------------------------------------------------------
+struct StepArgs {
+  Layout L;
+  State st;
+  int B;
+  const int32_t* actions;
+  float high, fea;
+  int reward_type, is_reset;
+  float* x;
+  int64_t* emc;
+  float* makespan;
+  float* incumbent;
+  float* reward;
+  uint8_t* done;
+  int32_t* pairs;
+  int32_t* npairs;
+  int32_t* status;
+  int pmax;
+  // mirrors of the per-instance scalars inside the packed host-result block (l2s_step_host)
+  float* makespan2;
+  float* incumbent2;
+  float* reward2;
+  uint8_t* done2;
+  // test introspection (l2s_export_state): evaluate only, no mutation
+  int export_only;
+  int32_t* ex_est;
+  int32_t* ex_lst;
+  int32_t* ex_path;
+  int32_t* ex_path_len;
+};
+
+__global__ void step_kernel(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_step[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * (blockDim.x >> 5) + w;
+  if (b >= a.B) return;
+  const Layout& L = a.L;
+  const Inst s = inst_view(L, smem_step + (size_t)w * L.bytes);
+  const int n = L.n, n1 = L.n1;
+
+  int a0 = 0, a1 = 0;
+  if (a.actions && !a.export_only) {
+    a0 = a.actions[2 * b];
+    a1 = a.actions[2 * b + 1];
+  }
+  int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
+  const int inc_old = a.st.inc[b], cur_old = a.st.cur[b];
+  stage_instance(L, s, a.st, b, lane, true);
+  __syncwarp();
+
+  int status = 0;
+  // 1. N5 swap (change_nxgraph_topology :318-354) + tabu update (:370-380)
+  {
+    int m, p, t;
+    const int r = apply_swap(L, s, a0, a1, lane, m, p, t);
+    if (r == 0) {
+      tabu0 = a1;
+      tabu1 = a0;
+      if (lane == 0) {
+        uint16_t* grow = a.st.seq + (size_t)b * L.seq_stride + m * L.n_j;
+        grow[p] = (uint16_t)a1;
+        grow[p + 1] = (uint16_t)a0;
+        uint32_t* gj = a.st.jf + (size_t)b * L.jf_words;
+        gj[a0 >> 5] = s.jf[a0 >> 5];
+        gj[a1 >> 5] = s.jf[a1 >> 5];
+        if (t) gj[t >> 5] = s.jf[t >> 5];
+        a.st.tabu[2 * b] = tabu0;
+        a.st.tabu[2 * b + 1] = tabu1;
+      }
+    } else if (r < 0) {
+      status = r;
+    }
+  }
+
+  // 2. evaluate (Evaluator.forward, env/message_passing_evl.py:161-199) + critical predecessors
+  const int ms = evaluate_instance<true>(L, s, lane, true);
+  if (ms < 0) {
+    status = -5;
+    if (lane == 0) {
+      record_error(a.st.err, -5, b);
+      if (a.status) a.status[b] = status;
+      if (a.npairs) a.npairs[b] = 0;
+      if (a.done) a.done[b] = 1;
+      if (a.done2) a.done2[b] = 1;
+    }
+    return;
+  }
+  const int32_t* fin = s.tq;
+  const int32_t* q = s.tq + L.n1p;
+  // latest start of S = min over job-first ops (:195 on the S row)
+  int qs = 0;
+  for (int j = lane; j < L.n_j; j += 32) qs = max(qs, q[j * L.n_m + 1]);
+  qs = __reduce_max_sync(kFull, qs);
+  const int lst_s = ms - qs;
+
+  // 3. node features x = [dur/high, est/c, lst/c] (env/environment.py:312), IEEE-RN float32 divisions
+  if (a.x) {
+    float* xo = a.x + (size_t)b * n1 * 3;
+    for (int e = lane; e < 3 * n1; e += 32) {
+      const int i = e / 3, c = e - 3 * i;
+      const int d = s.durw[i] & kDurMask;
+      int num;
+      if (c == 0) num = d;
+      else if (i == 0) num = c == 1 ? 0 : lst_s;
+      else if (i == n1 - 1) num = ms;
+      else num = c == 1 ? fin[i] - d : ms - q[i];
+      xo[e] = __fdiv_rn((float)num, c == 0 ? a.high : a.fea);
+    }
+  }
+  if (a.ex_est) {
+    for (int i = lane; i < n1; i += 32) {
+      const int d = s.durw[i] & kDurMask;
+      a.ex_est[(size_t)b * n1 + i] = i == 0 ? 0 : (i == n1 - 1 ? ms : fin[i] - d);
+      a.ex_lst[(size_t)b * n1 + i] = i == 0 ? lst_s : (i == n1 - 1 ? ms : ms - q[i]);
+    }
+  }
+  __syncwarp();
+
+  // 4. machine edges ascending by source (dag2pyg :300-305); q is dead now, reuse it as scratch
+  uint16_t* msu = reinterpret_cast<uint16_t*>(s.tq + L.n1p);   // [n1] machine successor per node
+  uint16_t* rp = msu + n1;                                      // [n] reversed critical path
+  if (a.emc) {
+    for (int m = 0; m < L.n_m; ++m) {
+      const uint16_t* row = s.seq + m * L.n_j;
+      for (int k = lane; k < L.n_j; k += 32) msu[row[k]] = (k + 1 < L.n_j) ? row[k + 1] : 0;
+    }
+    __syncwarp();
+    const long long off = (long long)b * n1;
+    long long* src = reinterpret_cast<long long*>(a.emc) + (size_t)b * L.e_mc;
+    long long* dst = src + (size_t)a.B * L.e_mc;
+    int cnt = 0;
+    for (int v0 = 1; v0 <= n; v0 += 32) {
+      const int v = v0 + lane;
+      const int sc = v <= n ? msu[v] : 0;
+      const unsigned bal = __ballot_sync(kFull, sc != 0);
+      if (sc) {
+        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+        src[pos] = off + v;
+        dst[pos] = off + sc;
+      }
+      cnt += __popc(bal);
+    }
+  }
+
+  // 5. critical path (nx.dag_longest_path, :77) and N5 move set (_get_pairs :84-105)
+  const int len = trace_path(L, s, ms, lane, rp);
+  if (a.ex_path) {
+    for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = rp[len - 1 - i];
+    if (lane == 0) a.ex_path_len[b] = len;
+  }
+  int32_t* po = a.pairs ? a.pairs + (size_t)b * a.pmax * 2 : nullptr;
+  const int pmax = a.pmax;
+  int np = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
+    if (po && idx < pmax) {
+      po[2 * idx] = u;
+      po[2 * idx + 1] = v;
+    }
+  });
+  if (np < 0) { status = status ? status : np; np = 0; }
+  if (np > pmax) { status = status ? status : -8; np = pmax; }
+
+  // 6. reward / incumbent / current (:359-367)
+  if (lane == 0) {
+    int reward, inc;
+    if (a.is_reset) {
+      reward = 0;
+      inc = ms;
+    } else {
+      reward = a.reward_type == 1 ? cur_old - ms : max(inc_old - ms, 0);
+      inc = min(inc_old, ms);
+    }
+    if (!a.export_only) {
+      a.st.cur[b] = ms;
+      a.st.inc[b] = inc;
+    }
+    if (a.makespan) a.makespan[b] = (float)ms;
+    if (a.incumbent) a.incumbent[b] = (float)inc;
+    if (a.reward) a.reward[b] = (float)reward;
+    if (a.done) a.done[b] = np == 0;
+    if (a.makespan2) a.makespan2[b] = (float)ms;
+    if (a.incumbent2) a.incumbent2[b] = (float)inc;
+    if (a.reward2) a.reward2[b] = (float)reward;
+    if (a.done2) a.done2[b] = np == 0;
+    if (a.npairs) a.npairs[b] = np;
+    if (a.status) a.status[b] = status;
+    if (status) record_error(a.st.err, status, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K fused steps with an on-device policy; state stays in shared memory for the whole launch.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMaxLog = 16;
+struct RunArgs {
+  Layout L;
+  State st;
+  int B;
+  int policy, K;
+  const int32_t* tape;
+  unsigned long long seed;
+  long long inst_off, itr0;
+  int32_t* taken;
+  int n_log;
+  int log_steps[kMaxLog];
+  float* inc_log;
+  int pmax;
+  int off_plist;   // byte offset (within the instance's smem) of the uint16 pair list [pmax][2]
+  int stride;      // shared-memory bytes per instance (state + pair list)
+};
+
+// locate the adjacent pair (a0,a1): machine row and position, or -1
+__device__ __forceinline__ bool locate_pair(const Layout& L, const Inst& s, int a0, int a1, int lane, int& m, int& p) {
+  if (a0 < 1 || a0 > L.n || a1 < 1 || a1 > L.n || a0 == a1) return false;
+  m = (int)s.mch[a0 - 1] - 1;
+  if ((int)s.mch[a1 - 1] - 1 != m) return false;
+  const uint16_t* row = s.seq + m * L.n_j;
+  p = -1;
+  for (int k0 = 0; k0 < L.n_j; k0 += 32) {
+    const int k = k0 + lane;
+    const unsigned hit = __ballot_sync(kFull, k < L.n_j && row[k] == a0);
+    if (hit) { p = k0 + __ffs(hit) - 1; break; }
+  }
+  return p >= 0 && p + 1 < L.n_j && row[p + 1] == a1;
+}
+
+__global__ void run_kernel(const __grid_constant__ RunArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_run[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * (blockDim.x >> 5) + w;
+  if (b >= a.B) return;
+  const Layout& L = a.L;
+  unsigned char* base = smem_run + (size_t)w * a.stride;
+  const Inst s = inst_view(L, base);
+  uint16_t* plist = reinterpret_cast<uint16_t*>(base + a.off_plist);
+  uint16_t* rp = reinterpret_cast<uint16_t*>(s.tq + L.n1p);   // backward half is unused here
+  const int pmax = a.pmax;
+
+  int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
+  int inc = a.st.inc[b], cur = a.st.cur[b];
+  stage_instance(L, s, a.st, b, lane, false);
+  __syncwarp();
+  int status = 0;
+  int ms = evaluate_instance<true>(L, s, lane, false);
+  if (ms < 0) status = -5;
+  int np = 0;
+  auto enumerate = [&]() {
+    const int len = trace_path(L, s, ms, lane, rp);
+    int c = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
+      if (idx < pmax) { plist[2 * idx] = (uint16_t)u; plist[2 * idx + 1] = (uint16_t)v; }
+    });
+    if (c < 0) { status = status ? status : c; c = 0; }
+    if (c > pmax) { status = status ? status : -8; c = pmax; }
+    __syncwarp();
+    return c;
+  };
+  if (!status) np = enumerate();
+  int li = 0;
+  for (int step = 0; step < a.K; ++step) {
+    int a0 = 0, a1 = 0;
+    if (!status) {
+      if (a.policy == 0) {
+        a0 = a.tape[((size_t)b * a.K + step) * 2];
+        a1 = a.tape[((size_t)b * a.K + step) * 2 + 1];
+      } else if (np > 0) {
+        int pick = 0;
+        if (a.policy == 1) {
+          pick = random_pick(a.seed, (uint64_t)(a.inst_off + b), (uint64_t)(a.itr0 + step), np);
+        } else {
+          // GREEDY: evaluate every neighbour, first minimum wins (conventional_baselines...:186-197)
+          int best = 0x7fffffff;
+          for (int i = 0; i < np; ++i) {
+            int m, p;
+            locate_pair(L, s, plist[2 * i], plist[2 * i + 1], lane, m, p);
+            uint16_t* row = s.seq + m * L.n_j;
+            __syncwarp();
+            if (lane == 0) { const uint16_t t0 = row[p]; row[p] = row[p + 1]; row[p + 1] = t0; }
+            fill_pending(L, s, lane, false);
+            __syncwarp();
+            const int nms = evaluate_instance<false>(L, s, lane, false);
+            if (lane == 0) { const uint16_t t0 = row[p]; row[p] = row[p + 1]; row[p + 1] = t0; }
+            __syncwarp();
+            if (nms >= 0 && nms < best) { best = nms; pick = i; }
+          }
+        }
+        a0 = plist[2 * pick];
+        a1 = plist[2 * pick + 1];
+      }
+      int m, p, t;
+      const int r = apply_swap(L, s, a0, a1, lane, m, p, t);
+      if (r == 0) {
+        tabu0 = a1;
+        tabu1 = a0;
+      } else if (r < 0) {
+        status = r;
+      }
+      if (!status && r == 0) {   // a dummy move leaves the schedule, its makespan and its move set unchanged
+        fill_pending(L, s, lane, false);
+        __syncwarp();
+        ms = evaluate_instance<true>(L, s, lane, false);
+        if (ms < 0) status = -5;
+      }
+      if (!status && r == 0) {
+        cur = ms;
+        inc = min(inc, ms);
+        np = enumerate();
+      }
+    }
+    if (a.taken && lane == 0) {
+      a.taken[((size_t)b * a.K + step) * 2] = a0;
+      a.taken[((size_t)b * a.K + step) * 2 + 1] = a1;
+    }
+    if (li < a.n_log && step + 1 == a.log_steps[li]) {
+      if (lane == 0) a.inc_log[(size_t)li * a.B + b] = (float)inc;
+      ++li;
+    }
+  }
+  // write the search state back
+  __syncwarp();
+  uint4* gs = reinterpret_cast<uint4*>(a.st.seq + (size_t)b * L.seq_stride);
+  const uint4* ss = reinterpret_cast<const uint4*>(s.seq);
+  for (int i = lane; i < L.seq_stride / 8; i += 32) gs[i] = ss[i];
+  uint32_t* gj = a.st.jf + (size_t)b * L.jf_words;
+  for (int i = lane; i < L.jf_words; i += 32) gj[i] = s.jf[i];
+  if (lane == 0) {
+    a.st.tabu[2 * b] = tabu0;
+    a.st.tabu[2 * b + 1] = tabu1;
+    a.st.cur[b] = cur;
+    a.st.inc[b] = inc;
+    if (status) record_error(a.st.err, status, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Stateless evaluator for COO input: drop-in for Evaluator.forward (env/message_passing_evl.py:161-199).
+//   pass 1 (coo_ingest_kernel): one thread per edge, coalesced int64 reads; conjunctive arcs are implicit in
+//           the node numbering and only counted, machine arcs are scattered into uint16 succ/pred arrays.
+//   pass 2 (coo_eval_kernel): one warp per graph, same wavefront as the environment but following the
+//           succ/pred chains (the machine of an operation is not part of this API).
+// ------------------------------------------------------------------------------------------------------
+struct CooWs {
+  uint16_t* msucc;      // [B][node_stride]
+  uint16_t* mpred;      // [B][node_stride]
+  unsigned long long* conj_count;
+  int32_t* flag;        // device status word
+};
+
+__global__ void coo_ingest_kernel(const long long* __restrict__ ei, long long E, int n_j, int n_m, long long B,
+                                  int node_stride, CooWs ws) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n_j * n_m, n1 = n + 2;
+  int conj = 0;
+  if (e < E) {
+    const long long u = ei[e], v = ei[E + e];
+    const long long bu = u / n1, bv = v / n1;
+    const int ul = (int)(u - bu * n1), vl = (int)(v - bv * n1);
+    if (u < 0 || v < 0 || bu != bv || bu >= B) {
+      atomicCAS(ws.flag, 0, -5);
+    } else if (ul == 0) {
+      if (vl >= 1 && vl <= n && (vl - 1) % n_m == 0) conj = 1; else atomicCAS(ws.flag, 0, -5);
+    } else if (vl == n + 1) {
+      if (ul >= 1 && ul <= n && ul % n_m == 0) conj = 1; else atomicCAS(ws.flag, 0, -5);
+    } else if (ul > n || vl == 0) {
+      atomicCAS(ws.flag, 0, -5);   // edge out of T or into S
+    } else if (vl == ul + 1 && ul % n_m != 0) {
+      conj = 1;
+    } else {
+      ws.msucc[bu * node_stride + ul] = (uint16_t)vl;
+      ws.mpred[bu * node_stride + vl] = (uint16_t)ul;
+    }
+  }
+  const unsigned bal = __ballot_sync(kFull, conj);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(ws.conj_count, (unsigned long long)__popc(bal));
+}
+
+// chain-following wavefront: lane walks a machine chain through nxt[] (msucc forward / mpred backward)
+__device__ __forceinline__ bool wavefront_chain(int n, int n1p, volatile int32_t* tq, const uint16_t* durw,
+                                                const uint16_t* nxt, int head, int dir, int& last) {
+  const int base = dir ? n1p : 0;
+  const int nbr = dir ? 1 : -1;
+  const int bflag = dir ? kLastFlag : kFirstFlag;
+  int prevval = 0, cur = head, dw = 0;
+  bool more = cur != 0;
+  if (more) dw = durw[cur];
+  int budget = n + 2;
+  while (true) {
+    if (more) {
+      int nb = tq[base + cur + nbr];
+      nb = (dw & bflag) ? 0 : nb;
+      if (nb >= 0) {
+        const int val = max(prevval, nb) + (dw & kDurMask);
+        tq[base + cur] = val;
+        prevval = val;
+        cur = nxt[cur];
+        more = cur != 0;
+        if (more) dw = durw[cur];
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(kFull, more)) break;
+    if (--budget < 0) { last = prevval; return false; }
+  }
+  last = prevval;
+  return true;
+}
+
+struct CooEvalArgs {
+  int n_j, n_m, n, n1, n1p, node_stride;
+  long long B;
+  const void* duration;
+  int dur_i64;
+  CooWs ws;
+  float* est;
+  float* lst;
+  float* ms;
+  int bytes;   // smem per graph
+  int off_tq, off_durw, off_succ, off_pred, off_heads;
+  long long expect_conj;
+};
+
+__global__ void coo_eval_kernel(const __grid_constant__ CooEvalArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_coo[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + w;
+  if (b >= a.B) return;
+  unsigned char* base = smem_coo + (size_t)w * a.bytes;
+  int32_t* tq = reinterpret_cast<int32_t*>(base + a.off_tq);
+  uint16_t* durw = reinterpret_cast<uint16_t*>(base + a.off_durw);
+  uint16_t* succ = reinterpret_cast<uint16_t*>(base + a.off_succ);
+  uint16_t* pred = reinterpret_cast<uint16_t*>(base + a.off_pred);
+  uint16_t* heads = reinterpret_cast<uint16_t*>(base + a.off_heads);   // [32] heads, [32] tails
+  const int n = a.n, n1 = a.n1, n_m = a.n_m;
+  if (b == 0 && lane == 0 && *a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
+
+  // stage: machine links (uint16, 16-byte vectors) and durations -> node words
+  const uint4* gs = reinterpret_cast<const uint4*>(a.ws.msucc + b * a.node_stride);
+  const uint4* gp = reinterpret_cast<const uint4*>(a.ws.mpred + b * a.node_stride);
+  for (int i = lane; i < a.node_stride / 8; i += 32) {
+    reinterpret_cast<uint4*>(succ)[i] = gs[i];
+    reinterpret_cast<uint4*>(pred)[i] = gp[i];
+  }
+  int bad = 0;
+  for (int i = lane; i < n1; i += 32) {
+    long long d = a.dur_i64 ? reinterpret_cast<const long long*>(a.duration)[b * n1 + i]
+                            : (long long)reinterpret_cast<const int32_t*>(a.duration)[b * n1 + i];
+    if (d < 0 || d > kDurMask) { bad = 1; d = 0; }
+    int word = (int)d;
+    if (i >= 1 && i <= n) {
+      const int pos = (i - 1) % n_m;
+      word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
+    } else if (d != 0) {
+      bad = 1;
+    }
+    durw[i] = (uint16_t)word;
+  }
+  const int4 pending = make_int4(-1, -1, -1, -1);
+  for (int i = lane; i < 2 * a.n1p / 4; i += 32) reinterpret_cast<int4*>(tq)[i] = pending;
+  __syncwarp();
+  // heads (no machine predecessor) and tails (no machine successor), ascending
+  int nh = 0, nt = 0, narc = 0;
+  for (int v0 = 1; v0 <= n; v0 += 32) {
+    const int v = v0 + lane;
+    const bool ish = v <= n && pred[v] == 0, ist = v <= n && succ[v] == 0;
+    const unsigned bh = __ballot_sync(kFull, ish), bt = __ballot_sync(kFull, ist);
+    const int ph = nh + __popc(bh & ((1u << lane) - 1u)), pt = nt + __popc(bt & ((1u << lane) - 1u));
+    if (ish && ph < 32) heads[ph] = (uint16_t)v;
+    if (ist && pt < 32) heads[32 + pt] = (uint16_t)v;
+    nh += __popc(bh);
+    nt += __popc(bt);
+    narc += __popc(__ballot_sync(kFull, v <= n && succ[v] != 0));
+  }
+  __syncwarp();
+  bad = __reduce_or_sync(kFull, bad);
+  // a complete selection has n_m chains covering all operations: n - n_m machine arcs
+  if (bad || nh != nt || nh > 32 || narc != n - nh) {
+    if (lane == 0) atomicCAS(a.ws.flag, 0, bad ? -6 : -5);
+    return;
+  }
+  bool ok;
+  int last = 0, fwd_last = 0;
+  if (nh <= 16) {
+    const int c = lane & 15, dir = lane >> 4;
+    const int head = c < nh ? heads[dir * 32 + c] : 0;
+    ok = wavefront_chain(n, a.n1p, tq, durw, dir ? pred : succ, head, dir, last);
+    fwd_last = dir ? 0 : last;
+  } else {
+    ok = wavefront_chain(n, a.n1p, tq, durw, succ, lane < nh ? heads[lane] : 0, 0, last);
+    fwd_last = last;
+    if (ok) {
+      int l2;
+      ok = wavefront_chain(n, a.n1p, tq, durw, pred, lane < nh ? heads[32 + lane] : 0, 1, l2);
+    }
+  }
+  // every operation must have been reached (a pure machine cycle has no head)
+  int pend = 0;
+  for (int v = 1 + lane; v <= n; v += 32) pend |= (tq[v] < 0) | (tq[a.n1p + v] < 0);
+  pend = __reduce_or_sync(kFull, pend);
+  if (!ok || pend) {
+    if (lane == 0) atomicCAS(a.ws.flag, 0, -5);
+    return;
+  }
+  const int ms = __reduce_max_sync(kFull, fwd_last);
+  int qs = 0;
+  for (int j = lane; j < a.n_j; j += 32) qs = max(qs, tq[a.n1p + j * n_m + 1]);
+  qs = __reduce_max_sync(kFull, qs);
+  float* eo = a.est + b * n1;
+  float* lo = a.lst + b * n1;
+  for (int i = lane; i < n1; i += 32) {
+    const int d = durw[i] & kDurMask;
+    eo[i] = (float)(i == 0 ? 0 : (i == n1 - 1 ? ms : tq[i] - d));
+    lo[i] = (float)(i == 0 ? ms - qs : (i == n1 - 1 ? ms : ms - tq[a.n1p + i]));
+  }
+  if (lane == 0) a.ms[b] = (float)ms;
+}
+
+}  // namespace l2s

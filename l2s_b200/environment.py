@@ -1,0 +1,311 @@
+"""Drop-in `JsspN5` / `BatchGraph` backed by the sm_100a kernels (mirror of the reference's
+env/environment.py:19-423 public surface: same constructor, `reset`, `step`, attributes, tensor layouts).
+
+The whole search state lives on the GPU inside an `l2s_handle`; one `step` is one kernel launch that
+applies the N5 swaps, re-evaluates every schedule, writes the policy inputs (x, edge_index_mc) and
+enumerates the next move sets.  Only the feasible pairs travel back to the host, because the reference API
+hands them to the policy as Python lists (model/actor.py:216-226).
+
+There is no CPU path: `device` must be a CUDA device and the CUDA library must be built.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import L2SError, StepIO
+
+
+class BatchGraph:
+    """Same 4-field holder as the reference (env/environment.py:19-36)."""
+
+    def __init__(self):
+        self.x = None
+        self.edge_index_pc = None
+        self.edge_index_mc = None
+        self.batch = None
+
+    def wrapper(self, x, edge_index_pc, edge_index_mc, batch):
+        self.x, self.edge_index_pc, self.edge_index_mc, self.batch = x, edge_index_pc, edge_index_mc, batch
+
+    def clean(self):
+        self.x = self.edge_index_pc = self.edge_index_mc = self.batch = None
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_view(ptr, shape, dtype):
+    n = int(np.prod(shape))
+    buf = (C.c_byte * (n * np.dtype(dtype).itemsize)).from_address(C.addressof(ptr.contents))
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def _raise_status(status, instance, where):
+    """Map device status codes to the exceptions the reference raises at the same place."""
+    if status == _capi.STATUS["SHORT_PATH"]:
+        raise IndexError("index 2 is out of bounds: critical path of two operations on one machine "
+                         "(instance %d; reference env/environment.py:89-90)" % instance)
+    if status == _capi.STATUS["ILLEGAL_ACTION"]:
+        try:
+            import networkx as nx
+            exc = nx.NetworkXError
+        except Exception:  # pragma: no cover
+            exc = L2SError
+        if exc is L2SError:
+            raise L2SError(status, where, instance)
+        raise exc("The edge of the action given for instance %d is not in the graph "
+                  "(not an adjacent pair on one machine)." % instance)
+    raise L2SError(status, where, instance)
+
+
+class JsspN5:
+    """N5 local-search environment for batches of JSSP instances (reference: env/environment.py:39-423)."""
+
+    def __init__(self, n_job, n_mch, low, high, reward_type='yaoxin', fea_norm_const=1000,
+                 evaluator_type='message-passing', pmax=32):
+        self.n_job = n_job
+        self.n_mch = n_mch
+        self.n_oprs = n_job * n_mch
+        self.low = low
+        self.high = high
+        self.itr = 0
+        self.instances = None
+        self.current_objs = None
+        self.incumbent_objs = None
+        self.tabu_size = 1
+        self.reward_type = reward_type
+        self.fea_norm_const = fea_norm_const
+        # 'message-passing' and 'CPM' give identical numbers in the reference (env/message_passing_evl.py
+        # :367-371); both are served by the same kernel here.
+        self.evaluator_type = evaluator_type
+        self.pmax = pmax
+        self.instance_offset = 0      # global index of the first instance (multi-GPU sharding)
+        self._h = None
+        self._key = None
+        self._device = None
+        self._const = None
+        self._lib = _capi.lib()
+
+    # -- handle management -----------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        if self._h is not None:
+            self._lib.l2s_destroy(self._h)
+            self._h = None
+
+    def _ensure_handle(self, B, device):
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError("l2s_b200 runs on CUDA devices only (no CPU fallback); got device=%r" % (device,))
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        key = (B, device.index)
+        if self._key != key:
+            self.close()
+            h = C.c_void_p()
+            _capi.check(self._lib.l2s_create(self.n_job, self.n_mch, B, self.pmax, device.index, C.byref(h)),
+                        "l2s_create")
+            self._h, self._key, self._device = h, key, device
+            p = [_capi.c_i32p(), _capi.c_i32p(), _capi.c_i32p(), _capi.c_f32p(), _capi.c_f32p(), _capi.c_f32p(),
+                 _capi.c_u8p(), _capi.c_i32p()]
+            _capi.check(self._lib.l2s_host_buffers(h, *[C.byref(q) for q in p]), "l2s_host_buffers")
+            pm = self._lib.l2s_pmax(h)
+            self._h_pairs = _np_view(p[0], (B, pm, 2), np.int32)
+            self._h_npairs = _np_view(p[1], (B,), np.int32)
+            self._h_status = _np_view(p[2], (B,), np.int32)
+            self._h_actions = _np_view(p[7], (B, 2), np.int32)
+            self._h_actions_ptr = C.cast(p[7], C.c_void_p)
+            n1 = self.n_oprs + 2
+            # static tensors, cached: conjunctive edges in the reference's order (env/environment.py:62-69,
+            # 301) and the node->graph map (:314)
+            first = torch.arange(self.n_job, dtype=torch.int64) * self.n_mch + 1
+            u = torch.arange(1, self.n_oprs + 1, dtype=torch.int64)
+            v = torch.where(u % self.n_mch != 0, u + 1, torch.full_like(u, self.n_oprs + 1))
+            pc = torch.stack([torch.cat([torch.zeros(self.n_job, dtype=torch.int64), u]), torch.cat([first, v])])
+            off = (torch.arange(B, dtype=torch.int64) * n1).view(B, 1, 1)
+            epc = (pc.unsqueeze(0) + off).permute(1, 0, 2).reshape(2, -1).contiguous().to(device)
+            batch = torch.arange(B, dtype=torch.int64).repeat_interleave(n1).to(device)
+            self._const = (epc, batch)
+        return device
+
+    # -- reference API ---------------------------------------------------------------------------------
+    def reset(self, instances, init_type, device, plot=False, init_solutions=None):
+        """instances: np.ndarray [B, 2, n_j, n_m] (durations, 1-based machines).  Returns
+        ((x, edge_index_pc, edge_index_mc, batch), feasible_actions, done) like env/environment.py:389-409.
+        `init_solutions` [B, n_m, n_j] (extension) installs given machine orders instead of a rule."""
+        instances = np.asarray(instances)
+        B = instances.shape[0]
+        assert instances.shape[1:] == (2, self.n_job, self.n_mch), "instances must be [B,2,n_j,n_m]"
+        device = self._ensure_handle(B, device)
+        stream = _stream_ptr(device)
+        self.instances = instances
+        di = torch.from_numpy(np.ascontiguousarray(instances.reshape(B, 2, -1)).astype(np.int32)).to(device)
+        dur, mch = di[:, 0].contiguous(), di[:, 1].contiguous()
+        _capi.check(self._lib.l2s_load_instances(self._h, _ptr(dur), _ptr(mch), self.instance_offset, stream),
+                    "l2s_load_instances")
+        if init_solutions is not None:
+            sol = torch.from_numpy(np.ascontiguousarray(np.asarray(init_solutions)).astype(np.int32)).to(device)
+            assert sol.shape == (B, self.n_mch, self.n_job)
+            _capi.check(self._lib.l2s_set_solution(self._h, _ptr(sol), stream), "l2s_set_solution")
+        elif init_type == 'plist':
+            sol = torch.from_numpy(self._plist_orders(instances)).to(device)
+            _capi.check(self._lib.l2s_set_solution(self._h, _ptr(sol), stream), "l2s_set_solution")
+        elif init_type in _capi.RULE:
+            _capi.check(self._lib.l2s_build_initial(self._h, _capi.RULE[init_type], int(self.high), stream),
+                        "l2s_build_initial")
+        else:
+            assert False, 'Initial solution type = "plist", "spt", "fdd-divide-mwkr".'
+        self._poll("reset")
+        self.itr = 0
+        state, _, fa, done = self._launch(None, device, is_reset=True)
+        return state, fa, done
+
+    def step(self, actions, device, plot=False):
+        """actions: list of B [a0, a1] ([0, 0] = dummy).  Returns (state, reward, feasible_actions, done)
+        like env/environment.py:356-387."""
+        if self.reward_type not in _capi.REWARD:
+            raise ValueError('reward type must be "yaoxin" or "consecutive".')
+        acts = np.asarray(actions, dtype=np.int32).reshape(-1, 2)
+        assert acts.shape[0] == self._key[0], "one action per instance"
+        out = self._launch(acts, self._device, is_reset=False)
+        self.itr = self.itr + 1
+        return out
+
+    def feasible_actions(self, device=None):
+        """Move sets of the current solutions (env/environment.py:411-423) from the last launch."""
+        return self._fa, self._flag
+
+    @property
+    def tabu_lists(self):
+        """list[B] of [[a1, a0]] (last move reversed) or [] -- env/environment.py:370-380."""
+        if self._h is None:
+            return None
+        B = self._key[0]
+        tabu = torch.empty((B, 2), dtype=torch.int32, device=self._device)
+        _capi.check(self._lib.l2s_export_state(self._h, None, None, None, None, _ptr(tabu), None, None, None,
+                                               _stream_ptr(self._device)), "l2s_export_state")
+        return [[] if (a == 0 and b == 0) else [[a, b]] for a, b in tabu.cpu().tolist()]
+
+    def solutions(self):
+        """Current machine orders [B, n_m, n_j] int32 (device tensor) -- extension."""
+        B = self._key[0]
+        out = torch.empty((B, self.n_mch, self.n_job), dtype=torch.int32, device=self._device)
+        _capi.check(self._lib.l2s_get_solution(self._h, _ptr(out), _stream_ptr(self._device)), "l2s_get_solution")
+        return out
+
+    def export_state(self):
+        """Test introspection: integer est/lst [B, n+2], critical paths, tabu, tie-break history."""
+        B, dev, n1 = self._key[0], self._device, self.n_oprs + 2
+        est = torch.empty((B, n1), dtype=torch.int32, device=dev)
+        lst = torch.empty((B, n1), dtype=torch.int32, device=dev)
+        path = torch.zeros((B, self.n_oprs), dtype=torch.int32, device=dev)
+        plen = torch.zeros((B,), dtype=torch.int32, device=dev)
+        tabu = torch.empty((B, 2), dtype=torch.int32, device=dev)
+        jf = torch.empty((B, n1), dtype=torch.uint8, device=dev)
+        ms = torch.empty((B,), dtype=torch.float32, device=dev)
+        inc = torch.empty((B,), dtype=torch.float32, device=dev)
+        _capi.check(self._lib.l2s_export_state(self._h, _ptr(est), _ptr(lst), _ptr(path), _ptr(plen), _ptr(tabu),
+                                               _ptr(jf), _ptr(ms), _ptr(inc), _stream_ptr(dev)), "l2s_export_state")
+        self._poll("export_state")
+        return dict(est=est, lst=lst, path=path, path_len=plen, tabu=tabu, jobfirst=jf, makespan=ms, incumbent=inc)
+
+    # -- fused rollouts (no host round trip inside the loop) -------------------------------------------
+    def run(self, policy, steps, tape=None, seed=0, log_steps=(), return_actions=False):
+        """K = `steps` fused steps in ONE launch with an on-device policy ('replay' with tape [B,K,2],
+        'random', 'greedy').  Returns (incumbents at log_steps [len(log_steps), B] float32 device tensor,
+        actions taken [B,K,2] int32 or None).  Call `observe()` afterwards for the policy inputs."""
+        B, dev = self._key[0], self._device
+        tape_t = None
+        if policy == 'replay':
+            tape_t = torch.as_tensor(np.asarray(tape), dtype=torch.int32).reshape(B, steps, 2).contiguous().to(dev)
+        taken = torch.zeros((B, steps, 2), dtype=torch.int32, device=dev) if return_actions else None
+        log_steps = [int(s) for s in log_steps]
+        logs = torch.zeros((len(log_steps), B), dtype=torch.float32, device=dev)
+        arr = (C.c_int32 * max(1, len(log_steps)))(*log_steps)
+        _capi.check(self._lib.l2s_run(self._h, _capi.POLICY[policy], int(steps), _ptr(tape_t), int(seed),
+                                      _ptr(taken), arr, len(log_steps), _ptr(logs) if log_steps else None,
+                                      _stream_ptr(dev)), "l2s_run")
+        self._poll("run")
+        self.itr += int(steps)
+        return logs, taken
+
+    def observe(self):
+        """Re-evaluate without moving (a launch without actions changes neither the incumbent nor the step
+        counter): refreshes current/incumbent tensors and returns (state, feasible_actions, done)."""
+        state, _, fa, done = self._launch(None, self._device, is_reset=False)
+        return state, fa, done
+
+    # -- internals -------------------------------------------------------------------------------------
+    def _plist_orders(self, instances):
+        """'plist' initial solutions (env/environment.py:140-177,391-393): one random priority list of job
+        ids shared by the batch; every machine processes its operations in list order."""
+        B = instances.shape[0]
+        plist = np.random.permutation(np.arange(self.n_job).repeat(self.n_mch))
+        nxt = np.zeros(self.n_job, dtype=np.int64)
+        fill = np.zeros((B, self.n_mch), dtype=np.int64)
+        out = np.zeros((B, self.n_mch, self.n_job), dtype=np.int32)
+        rows = np.arange(B)
+        for j in plist:
+            m = instances[:, 1, j, nxt[j]].astype(np.int64) - 1
+            out[rows, m, fill[rows, m]] = j * self.n_mch + nxt[j] + 1
+            fill[rows, m] += 1
+            nxt[j] += 1
+        return out
+
+    def _poll(self, where):
+        inst = C.c_int32(0)
+        st = self._lib.l2s_poll_error(self._h, C.byref(inst), _stream_ptr(self._device))
+        if st < 0:
+            _raise_status(st, inst.value, where)
+
+    def _launch(self, acts, device, is_reset):
+        B = self._key[0]
+        n1 = self.n_oprs + 2
+        e_mc = self.n_mch * (self.n_job - 1)
+        x = torch.empty((B * n1, 3), dtype=torch.float32, device=device)
+        emc = torch.empty((2, B * e_mc), dtype=torch.int64, device=device)
+        ms = torch.empty((B, 1), dtype=torch.float32, device=device)
+        inc = torch.empty((B, 1), dtype=torch.float32, device=device)
+        reward = torch.empty((B, 1), dtype=torch.float32, device=device)
+        done = torch.empty((B, 1), dtype=torch.bool, device=device)
+        io = StepIO(actions=None, high=float(self.high), fea_norm_const=float(self.fea_norm_const),
+                    reward_type=_capi.REWARD.get(self.reward_type, 0), is_reset=1 if is_reset else 0,
+                    x=x.data_ptr(), edge_index_mc=emc.data_ptr(), makespan=ms.data_ptr(), incumbent=inc.data_ptr(),
+                    reward=reward.data_ptr(), done=done.data_ptr(), pairs=None, npairs=None, status=None)
+        a_ptr = None
+        if acts is not None:
+            self._h_actions[:] = acts
+            a_ptr = self._h_actions_ptr
+        _capi.check(self._lib.l2s_step_host(self._h, C.byref(io), a_ptr, None, None, None, None, None, None,
+                                            _stream_ptr(device)), "l2s_step")
+        status = self._h_status
+        if status.any():
+            b = int(np.nonzero(status)[0][0])
+            # drain the sticky device error word so that the next call starts clean
+            self._lib.l2s_poll_error(self._h, None, _stream_ptr(device))
+            _raise_status(int(status[b]), b, "step")
+        self.current_objs = ms
+        self.incumbent_objs = inc
+        npairs = self._h_npairs
+        mask = np.arange(self._h_pairs.shape[1])[None, :] < npairs[:, None]
+        flat = self._h_pairs[mask].tolist()
+        ends = np.cumsum(npairs).tolist()
+        fa, s = [], 0
+        for e in ends:
+            fa.append(flat[s:e] if e > s else [[0, 0]])
+            s = e
+        self._fa = fa
+        self._flag = ~done
+        return (x, self._const[0], emc, self._const[1]), reward, fa, done

@@ -1,0 +1,54 @@
+"""Drop-in `Evaluator` (reference: env/message_passing_evl.py:156-199) backed by the sm_100a kernels.
+
+`Evaluator().forward(edge_index, duration, n_j, n_m)` takes the same COO edge list (any edge order,
+conjunctive + machine arcs of a batch of complete selections, graphs offset by n_j*n_m+2) and durations
+([N,1] int32/int64, 0 for S and T) and returns `(est [N,1], lst [N,1], make_span [B,1])` as float32 tensors
+holding the same integer values the reference's iterated max-aggregation converges to.
+"""
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import L2SError
+
+
+class Evaluator:
+    def __init__(self):
+        self._lib = _capi.lib()
+        self._ws = None
+        self._flag = None
+
+    def forward(self, edge_index, duration, n_j, n_m):
+        if not edge_index.is_cuda or not duration.is_cuda:
+            raise RuntimeError("l2s_b200.Evaluator runs on CUDA tensors only (no CPU fallback)")
+        device = edge_index.device
+        n1 = n_j * n_m + 2
+        N = duration.shape[0]
+        if N % n1 != 0:
+            raise ValueError("duration has %d rows, not a multiple of n_j*n_m+2 = %d" % (N, n1))
+        B = N // n1
+        ei = edge_index.contiguous()
+        if ei.dtype != torch.int64:
+            ei = ei.to(torch.int64)
+        dur = duration.reshape(-1).contiguous()
+        if dur.dtype not in (torch.int32, torch.int64):
+            dur = dur.to(torch.int64)
+        need = self._lib.l2s_eval_coo_workspace_bytes(n_j, n_m, B)
+        _capi.check(need, "l2s_eval_coo_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        est = torch.empty((N, 1), dtype=torch.float32, device=device)
+        lst = torch.empty((N, 1), dtype=torch.float32, device=device)
+        ms = torch.empty((B, 1), dtype=torch.float32, device=device)
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _capi.check(self._lib.l2s_eval_coo(
+            C.c_void_p(ei.data_ptr()), ei.shape[1], C.c_void_p(dur.data_ptr()), 1 if dur.dtype == torch.int64 else 0,
+            n_j, n_m, B, C.c_void_p(est.data_ptr()), C.c_void_p(lst.data_ptr()), C.c_void_p(ms.data_ptr()),
+            C.c_void_p(self._ws.data_ptr()), self._ws.numel(), C.c_void_p(self._flag.data_ptr()),
+            device.index if device.index is not None else torch.cuda.current_device(), stream), "l2s_eval_coo")
+        flag = int(self._flag.item())   # the reference synchronises 2*depth times per call; we do it once
+        if flag < 0:
+            raise L2SError(flag, "Evaluator.forward")
+        return est, lst, ms

@@ -1,0 +1,165 @@
+"""GPU parity: the CUDA environment (through the C-ABI via the Python drop-in) against the golden vectors
+generated from the unmodified reference (tests/golden/traj_*.npz, made by oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs_from_fa(fa, pmax):
+    B = len(fa)
+    cnt = np.zeros(B, dtype=np.int32)
+    out = np.zeros((B, pmax, 2), dtype=np.int32)
+    for b, f in enumerate(fa):
+        if f == [[0, 0]]:
+            continue
+        cnt[b] = len(f)
+        out[b, :len(f)] = np.array(f)
+    return out, cnt
+
+
+@pytest.mark.parametrize("name", golden_names("traj_"))
+def test_trajectory_matches_reference(name):
+    from l2s_b200 import JsspN5
+    g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
+    n_j, n_m, high, fea = [int(v) for v in g["meta"]]
+    inst = g["instances"]
+    B, K = inst.shape[0], g["tape"].shape[1]
+    pmax = g["pairs"].shape[2]
+    env = JsspN5(n_j, n_m, 1, high, reward_type=str(g["reward_type"]), fea_norm_const=fea)
+    state, fa, done = env.reset(inst, str(g["init_type"]), "cuda", init_solutions=g["mseq0"])
+
+    def check(k, state, fa, done):
+        p, c = _pairs_from_fa(fa, pmax)
+        assert np.array_equal(c, g["npairs"][k]), "npairs step %d" % k
+        assert np.array_equal(p, g["pairs"][k]), "pairs step %d" % k
+        assert np.array_equal(done.cpu().numpy().reshape(-1), g["done"][k])
+        assert np.array_equal(env.current_objs.cpu().numpy().reshape(-1).astype(np.int32), g["makespan"][k])
+        assert np.array_equal(env.incumbent_objs.cpu().numpy().reshape(-1), g["incumbent"][k])
+        ex = env.export_state()
+        assert np.array_equal(ex["est"].cpu().numpy(), g["est"][k]), "est step %d" % k
+        assert np.array_equal(ex["lst"].cpu().numpy(), g["lst"][k]), "lst step %d" % k
+
+    check(0, state, fa, done)
+    assert state[0].dtype == torch.float32 and state[1].dtype == torch.int64 and state[2].dtype == torch.int64
+    assert np.array_equal(state[0].cpu().numpy(), g["x_first"])          # bit-exact float32 features
+    assert np.array_equal(state[1].cpu().numpy(), g["epc"])
+    assert np.array_equal(state[2].cpu().numpy(), g["emc_first"])
+    assert np.array_equal(state[3].cpu().numpy(), g["batch"])
+    for k in range(K):
+        acts = g["tape"][:, k].tolist()
+        state, reward, fa, done = env.step(acts, "cuda")
+        assert np.array_equal(reward.cpu().numpy().reshape(-1), g["reward"][k]), "reward step %d" % k
+        check(k + 1, state, fa, done)
+        assert env.itr == k + 1
+    assert np.array_equal(state[0].cpu().numpy(), g["x_last"])
+    assert np.array_equal(state[2].cpu().numpy(), g["emc_last"])
+    # tabu list = last applied move reversed
+    last = g["tape"][:, K - 1]
+    tl = env.tabu_lists
+    for b in range(B):
+        if last[b].any():
+            assert tl[b] == [[int(last[b, 1]), int(last[b, 0])]]
+
+
+def test_evaluator_coo_matches_reference():
+    from l2s_b200 import Evaluator
+    g = np.load(os.path.join(GOLDEN, "eval_coo.npz"))
+    ev = Evaluator()
+    for tag in ("6x4", "10x10", "20x15", "30x20"):
+        n_j, n_m, B = [int(v) for v in g["shape_" + tag]]
+        ei = torch.from_numpy(g["ei_" + tag]).cuda()
+        for dt in (torch.int32, torch.int64):
+            dur = torch.from_numpy(g["dur_" + tag]).to(dt).cuda()
+            est, lst, ms = ev.forward(ei, dur, n_j, n_m)
+            assert est.dtype == torch.float32 and est.shape == (B * (n_j * n_m + 2), 1) and ms.shape == (B, 1)
+            assert np.array_equal(est.cpu().numpy(), g["est_" + tag])
+            assert np.array_equal(lst.cpu().numpy(), g["lst_" + tag])
+            assert np.array_equal(ms.cpu().numpy(), g["ms_" + tag])
+
+
+@pytest.mark.parametrize("name", golden_names("traj_"))
+def test_initial_solution_builder(name):
+    """l2s_build_initial == the reference's _rules_solver whenever no priority tie occurred (the reference
+    breaks ties with np.random.choice), and == the oracle's first-min rule always."""
+    from l2s_b200 import JsspN5
+    from oracle import l2s_oracle as O
+    g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
+    n_j, n_m, high, fea = [int(v) for v in g["meta"]]
+    inst = g["instances"]
+    env = JsspN5(n_j, n_m, 1, high)
+    env.reset(inst, str(g["init_type"]), "cuda")
+    got = env.solutions().cpu().numpy()
+    for b in range(inst.shape[0]):
+        want, ties = O.rules_solver(inst[b, 0], inst[b, 1], str(g["init_type"]), high)
+        assert np.array_equal(got[b], want), "instance %d differs from the oracle builder" % b
+        if g["init_ties"][b] == 0:
+            assert np.array_equal(got[b], g["mseq0"][b]), "instance %d differs from the reference reset" % b
+
+
+@pytest.mark.parametrize("name", ["6x6_ties", "10x10", "20x15", "20x15_ties", "30x20"])
+def test_fused_run_replay_and_random(name):
+    """l2s_run (K steps, one launch) reproduces the per-step path and the reference trajectory."""
+    from l2s_b200 import JsspN5
+    from oracle import l2s_oracle as O
+    g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
+    n_j, n_m, high, fea = [int(v) for v in g["meta"]]
+    inst, tape = g["instances"], g["tape"]
+    B, K = tape.shape[0], tape.shape[1]
+    env = JsspN5(n_j, n_m, 1, high)
+    env.reset(inst, "fdd-divide-mwkr", "cuda", init_solutions=g["mseq0"])
+    logs, taken = env.run("replay", K, tape=tape, log_steps=[1, K // 2, K], return_actions=True)
+    assert np.array_equal(taken.cpu().numpy(), tape)
+    inc = g["incumbent"]
+    assert np.array_equal(logs.cpu().numpy(), np.stack([inc[1], inc[K // 2], inc[K]]))
+    state, fa, done = env.observe()
+    assert np.array_equal(state[0].cpu().numpy(), g["x_last"])
+    assert np.array_equal(env.current_objs.cpu().numpy().reshape(-1).astype(np.int32), g["makespan"][K])
+    assert env.itr == K
+    # RANDOM policy against the oracle driven by the same counter-based RNG
+    env.instance_offset = 1000
+    env.reset(inst, "fdd-divide-mwkr", "cuda", init_solutions=g["mseq0"])
+    K2 = min(K, 40)
+    logs, taken = env.run("random", K2, seed=12345, log_steps=[K2], return_actions=True)
+    oenv = O.OracleEnv(n_j, n_m, 1, high)
+    _, ofa, _ = oenv.reset(inst, mseq=g["mseq0"])
+    otaken, ologs = O.run_policy(oenv, ofa, "random", K2, seed=12345, inst_offset=1000, log_steps=[K2])
+    assert np.array_equal(taken.cpu().numpy(), otaken)
+    assert np.array_equal(logs.cpu().numpy(), ologs)
+
+
+def test_illegal_action_and_errors():
+    import networkx as nx
+    from l2s_b200 import JsspN5
+    g = np.load(os.path.join(GOLDEN, "traj_10x5.npz"))
+    inst = g["instances"]
+    env = JsspN5(10, 5, 1, 99)
+    state, fa, done = env.reset(inst, "fdd-divide-mwkr", "cuda", init_solutions=g["mseq0"])
+    acts = [f[0] for f in fa]
+    acts[2] = [1, 2]      # same job: never an adjacent machine pair
+    with pytest.raises(nx.NetworkXError):
+        env.step(acts, "cuda")
+    with pytest.raises(AssertionError):
+        env.reset(inst, "no-such-rule", "cuda")
+    bad = JsspN5(10, 5, 1, 99, reward_type="nope")
+    bad.reset(inst, "fdd-divide-mwkr", "cuda")
+    with pytest.raises(ValueError):
+        bad.step([[0, 0]] * inst.shape[0], "cuda")
+    with pytest.raises(RuntimeError):
+        JsspN5(10, 5, 1, 99).reset(inst, "fdd-divide-mwkr", "cpu")
+
+
+def test_dummy_actions_freeze_state():
+    from l2s_b200 import JsspN5
+    g = np.load(os.path.join(GOLDEN, "traj_10x5.npz"))
+    inst = g["instances"]
+    env = JsspN5(10, 5, 1, 99)
+    s0, fa0, _ = env.reset(inst, "fdd-divide-mwkr", "cuda", init_solutions=g["mseq0"])
+    s1, r, fa1, _ = env.step([[0, 0]] * inst.shape[0], "cuda")
+    assert torch.equal(s0[0], s1[0]) and torch.equal(s0[2], s1[2]) and fa0 == fa1
+    assert float(r.abs().sum()) == 0 and env.itr == 1
