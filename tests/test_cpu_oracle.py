@@ -1,0 +1,126 @@
+"""CPU suite (no GPU): the oracle against the golden vectors produced by the unmodified reference, the host
+logic, and the C-ABI library's exported symbols."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_names
+from oracle import l2s_oracle as O
+
+
+def _fa_list(pairs, npairs):
+    return [[list(map(int, p)) for p in pairs[b, :npairs[b]]] if npairs[b] else [[0, 0]] for b in range(len(npairs))]
+
+
+@pytest.mark.parametrize("name", golden_names("traj_"))
+def test_oracle_replays_reference_trajectory(name):
+    g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
+    n_j, n_m, high, fea = [int(v) for v in g["meta"]]
+    K = g["tape"].shape[1]
+    env = O.OracleEnv(n_j, n_m, 1, high, reward_type=str(g["reward_type"]), fea_norm_const=fea)
+    state, fa, done = env.reset(g["instances"], mseq=g["mseq0"])
+    assert np.array_equal(state[0], g["x_first"]) and np.array_equal(state[2], g["emc_first"])
+    assert np.array_equal(state[1], g["epc"]) and np.array_equal(state[3], g["batch"])
+    for k in range(K + 1):
+        assert [[list(map(int, p)) for p in f] for f in fa] == _fa_list(g["pairs"][k], g["npairs"][k])
+        assert np.array_equal(done.reshape(-1), g["done"][k])
+        assert np.array_equal(env.current_objs.reshape(-1).astype(np.int32), g["makespan"][k])
+        assert np.array_equal(env.incumbent_objs.reshape(-1), g["incumbent"][k])
+        assert np.array_equal(np.stack([i.est for i in env.insts]), g["est"][k])
+        assert np.array_equal(np.stack([i.lst for i in env.insts]), g["lst"][k])
+        if k < K:
+            state, reward, fa, done = env.step(g["tape"][:, k].tolist())
+            assert np.array_equal(reward.reshape(-1), g["reward"][k])
+    assert np.array_equal(state[0], g["x_last"]) and np.array_equal(state[2], g["emc_last"])
+
+
+@pytest.mark.parametrize("name", golden_names("traj_"))
+def test_oracle_initial_solution_equals_reference_without_ties(name):
+    g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
+    inst = g["instances"]
+    checked = 0
+    for b in range(inst.shape[0]):
+        mseq, ties = O.rules_solver(inst[b, 0], inst[b, 1], str(g["init_type"]), 99)
+        assert ties == g["init_ties"][b]
+        if ties == 0:
+            assert np.array_equal(mseq, g["mseq0"][b])
+            checked += 1
+    if name in ("10x5", "8x3_consecutive"):
+        assert checked == inst.shape[0]
+
+
+def test_oracle_jacobi_evaluator_equals_reference():
+    g = np.load(os.path.join(GOLDEN, "eval_coo.npz"))
+    for tag in ("6x4", "10x10", "20x15"):
+        n_j, n_m, B = [int(v) for v in g["shape_" + tag]]
+        est, lst, ms = O.evaluate_coo_jacobi(g["ei_" + tag], g["dur_" + tag], n_j, n_m)
+        assert np.array_equal(est, g["est_" + tag].reshape(-1))
+        assert np.array_equal(lst, g["lst_" + tag].reshape(-1))
+        assert np.array_equal(ms, g["ms_" + tag].reshape(-1))
+
+
+@pytest.mark.parametrize("ds,steps", [("ft6x6", 500), ("la10x5", 100), ("tai20x15", 10)])
+def test_oracle_greedy_equals_reference(ds, steps):
+    """Greedy policy known-answer test: incumbents logged by the reference's Greedy_baselines (and, at 500
+    steps, the reference's own stored result array)."""
+    g = np.load(os.path.join(GOLDEN, "greedy_%s.npz" % ds))
+    inst = g["instances"]
+    n_j, n_m = inst.shape[2], inst.shape[3]
+    logs = [int(s) for s in g["log_steps"] if s <= steps]
+    env = O.OracleEnv(n_j, n_m, 1, 99)
+    _, fa, _ = env.reset(inst, mseq=g["mseq0"])
+    _, got = O.run_policy(env, fa, "greedy", steps, log_steps=logs)
+    assert np.array_equal(got, g["incumbents"][:len(logs)])
+    if steps >= 500:
+        assert np.array_equal(got[logs.index(500)], g["stored_rows"][0])
+
+
+def test_n5_pair_rules_and_quirk():
+    mch = np.array([1, 1, 1, 2, 2, 3, 3, 3, 3])      # machines of ops 1..9 (path = ops in order)
+    path = list(range(1, 10))
+    # first block (len 3): only its last pair; block of 2: its pair; last block (len 4): only its first pair
+    assert O.n5_pairs(path, mch, None) == [[2, 3], [4, 5], [6, 7]]
+    assert O.n5_pairs(path, mch, (4, 5)) == [[2, 3], [6, 7]]
+    assert O.n5_pairs([1, 2, 4], mch, None) == [[1, 2]]
+    with pytest.raises(IndexError):
+        O.n5_pairs([1, 2], mch, None)
+
+
+def test_random_pick_is_stable():
+    assert [O.random_pick(7, i, s, 9) for i, s in ((0, 0), (1, 0), (0, 1), (12345, 499))] == \
+        [O.random_pick(7, i, s, 9) for i, s in ((0, 0), (1, 0), (0, 1), (12345, 499))]
+    assert all(0 <= O.random_pick(3, i, 5, 4) < 4 for i in range(200))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/l2s_b200.h declares (no compute calls)."""
+    from l2s_b200 import _capi, build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "l2s_b200.h")).read()
+    declared = set(re.findall(r"\b(l2s_[a-z0-9_]+)\s*\(", header))
+    declared -= {"l2s_handle_s"}
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "library does not export %s" % name
+    assert declared == set(_capi.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    assert _capi.lib().l2s_version() >= 100
+    assert _capi.lib().l2s_status_string(-4).decode().startswith("illegal action")
+    assert _capi.lib().l2s_eval_coo_workspace_bytes(20, 15, 8) > 0
+
+
+def test_product_has_no_cpu_path_and_never_imports_the_oracle():
+    import l2s_b200
+    src_dir = os.path.dirname(l2s_b200.__file__)
+    for dirpath, _, files in os.walk(src_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+    env = l2s_b200.JsspN5(6, 6, 1, 99)
+    inst = np.load(os.path.join(GOLDEN, "traj_6x6_ties.npz"))["instances"]
+    with pytest.raises(RuntimeError):
+        env.reset(inst, "fdd-divide-mwkr", "cpu")
