@@ -254,6 +254,12 @@ def run_ours(args, rank, world, local_rank):
     st = torch.stack([o["status"] for o in outs])
     assert int(st.abs().sum()) == 0, "device-side error during the timed region"
     pbar = float(torch.stack([o["npairs"] for o in outs]).float().mean())
+    if args.device_only:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"shape": args.shape, "batch": B, "launch_us": 1e3 * ms_dev / K,
+                              "value": world * B * K / (ms_dev / 1e3)}), flush=True)
+        return
 
     # ---- phase 2: end to end through the Python drop-in API ------------------------------------------
     # sync the Python-side step counters with the C handle, then time JsspN5.step with host lists
@@ -377,6 +383,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="kernel-only timing (skips the e2e phases)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -48,7 +48,7 @@ typedef enum {
                                      NetworkXError from remove_edge, env/environment.py:348             */
   L2S_ERR_BAD_GRAPH = -5,         /* cyclic selection / malformed COO (reference: evaluator runs N sweeps
                                      and nx.dag_longest_path raises)                                    */
-  L2S_ERR_DURATION_RANGE = -6,    /* durations must be in [1, 16383] and n*max(dur) < 2^24               */
+  L2S_ERR_DURATION_RANGE = -6,    /* durations must be in [1, 4095], sum per instance < 2^24              */
   L2S_ERR_MACHINE_ROWS = -7,      /* every job must visit machines 1..n_m exactly once                    */
   L2S_ERR_PAIR_OVERFLOW = -8,     /* more N5 pairs than `pmax`; recreate the handle with a larger pmax    */
   L2S_ERR_SHORT_PATH = -9,        /* critical path of exactly two ops on one machine; the reference raises

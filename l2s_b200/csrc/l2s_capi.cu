@@ -36,19 +36,15 @@ Layout make_layout(int n_j, int n_m) {
   L.n = n_j * n_m;
   L.n1 = L.n + 2;
   L.n1p = ru(L.n1, 4);
-  L.seq_stride = ru(L.n, 8);
+  L.walk_stride = ru(L.n, 4);
   L.node_stride = ru(L.n1, 8);
   L.mch_stride = ru(L.n, 16);
-  L.jf_words = ru((L.n1 + 31) / 32, 4);
   L.e_mc = n_m * (n_j - 1);
   int off = 0;
   L.off_tq = off;   off += 2 * L.n1p * 4;
-  L.off_seq = off;  off += L.seq_stride * 2;
+  L.off_walk = off; off += L.walk_stride * 4;
   L.off_durw = off; off += L.node_stride * 2;
   L.off_crit = off; off += L.node_stride * 2;
-  L.off_mch = off;  off += L.mch_stride;
-  L.off_jf = off;   off += L.jf_words * 4;
-  L.off_misc = off; off += kMiscInts * 4;
   L.bytes = ru(off, 16);
   return L;
 }
@@ -80,6 +76,7 @@ struct l2s_handle_s {
   long long itr;
   int warps_step, warps_run, warps_init;
   size_t run_stride;
+  int run_off_where, run_off_plist;
   InitLayout IL;
   // staging for the host-driven step
   int32_t* d_actions;
@@ -100,7 +97,7 @@ const char* l2s_status_string(int s) {
     case L2S_ERR_UNSUPPORTED_SHAPE: return "unsupported shape (n_m > 32, n+2 > 65535 or state exceeds shared memory)";
     case L2S_ERR_ILLEGAL_ACTION: return "illegal action: not an adjacent pair on one machine";
     case L2S_ERR_BAD_GRAPH: return "cyclic or malformed disjunctive graph";
-    case L2S_ERR_DURATION_RANGE: return "duration out of range [1,16383] or total duration >= 2^24";
+    case L2S_ERR_DURATION_RANGE: return "duration out of range [1,4095] or total duration >= 2^24";
     case L2S_ERR_MACHINE_ROWS: return "every job must visit machines 1..n_m exactly once";
     case L2S_ERR_PAIR_OVERFLOW: return "more N5 pairs than pmax";
     case L2S_ERR_SHORT_PATH: return "critical path of two operations on one machine (reference raises IndexError)";
@@ -123,7 +120,9 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->pmax = pmax;
   h->L = make_layout(n_j, n_m);
   const Layout& L = h->L;
-  h->run_stride = ru((long long)L.bytes + (long long)pmax * 4, 16);
+  h->run_off_where = L.bytes;
+  h->run_off_plist = L.bytes + L.node_stride * 2;
+  h->run_stride = ru((long long)h->run_off_plist + (long long)pmax * 4, 16);
   // initial-solution builder layout
   {
     InitLayout& I = h->IL;
@@ -139,26 +138,31 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
     I.bytes = off;
   }
   h->warps_step = pick_warps(L.bytes);
+  if (const char* e = getenv("L2S_WARPS_STEP")) { int v = atoi(e); if (v > 0 && (size_t)v * L.bytes <= kSmemPerCtaMax) h->warps_step = v; }
   h->warps_run = pick_warps(h->run_stride);
   h->warps_init = pick_warps(h->IL.bytes);
   if (!h->warps_step || !h->warps_run || !h->warps_init) { free(h); return L2S_ERR_UNSUPPORTED_SHAPE; }
   CU(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
   CU(cudaFuncSetAttribute(run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
   CU(cudaFuncSetAttribute(build_initial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
+  // these kernels live in shared memory, not in L1: ask for the largest shared-memory carve-out
+  CU(cudaFuncSetAttribute(step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(run_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(build_initial_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const size_t B = batch;
   State& st = h->st;
   CU(cudaMalloc(&st.durw, B * L.node_stride * 2));
   CU(cudaMalloc(&st.mch, B * L.mch_stride));
-  CU(cudaMalloc(&st.seq, B * L.seq_stride * 2));
-  CU(cudaMalloc(&st.jf, B * L.jf_words * 4));
+  CU(cudaMalloc(&st.walk, B * L.walk_stride * 4));
+  CU(cudaMalloc(&st.where, B * L.node_stride * 2));
   CU(cudaMalloc(&st.tabu, B * 8));
   CU(cudaMalloc(&st.cur, B * 4));
   CU(cudaMalloc(&st.inc, B * 4));
   CU(cudaMalloc(&st.err, 4));
   CU(cudaMemset(st.durw, 0, B * L.node_stride * 2));
   CU(cudaMemset(st.mch, 0, B * L.mch_stride));
-  CU(cudaMemset(st.seq, 0, B * L.seq_stride * 2));
-  CU(cudaMemset(st.jf, 0, B * L.jf_words * 4));
+  CU(cudaMemset(st.walk, 0, B * L.walk_stride * 4));
+  CU(cudaMemset(st.where, 0, B * L.node_stride * 2));
   CU(cudaMemset(st.tabu, 0, B * 8));
   CU(cudaMemset(st.cur, 0, B * 4));
   CU(cudaMemset(st.inc, 0, B * 4));
@@ -186,7 +190,7 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
 int l2s_destroy(l2s_handle h) {
   if (!h) return L2S_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->st.durw); cudaFree(h->st.mch); cudaFree(h->st.seq); cudaFree(h->st.jf);
+  cudaFree(h->st.durw); cudaFree(h->st.mch); cudaFree(h->st.walk); cudaFree(h->st.where);
   cudaFree(h->st.tabu); cudaFree(h->st.cur); cudaFree(h->st.inc); cudaFree(h->st.err);
   cudaFree(h->d_pack); cudaFreeHost(h->h_pack); cudaFree(h->d_actions); cudaFreeHost(h->h_actions);
   free(h);
@@ -367,7 +371,8 @@ int l2s_run(l2s_handle h, int policy, int K, const int32_t* tape, uint64_t seed,
   }
   a.inc_log = incumbent_log;
   a.pmax = h->pmax;
-  a.off_plist = h->L.bytes;
+  a.off_where = h->run_off_where;
+  a.off_plist = h->run_off_plist;
   a.stride = (int)h->run_stride;
   const int W = h->warps_run;
   run_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * h->run_stride, (cudaStream_t)stream>>>(a);
@@ -458,6 +463,7 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   static bool attr_set[64] = {false};
   if (device >= 0 && device < 64 && !attr_set[device]) {
     CU(cudaFuncSetAttribute(coo_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
+    CU(cudaFuncSetAttribute(coo_eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[device] = true;
   }
   CU(cudaMemsetAsync(workspace, 0, 2 * links + 16, s));

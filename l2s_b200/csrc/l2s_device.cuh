@@ -2,82 +2,111 @@
 //
 // Execution model: ONE WARP OWNS ONE INSTANCE.  The instance's whole search state lives in that warp's
 // slice of shared memory, so no block-level barrier is ever needed; every synchronisation is a
-// __syncwarp / ballot.  A CTA is just a bundle of independent warps (so that > 32 instances fit one SM).
+// __syncwarp / vote.  A CTA is just a bundle of independent warps (so that > 32 instances fit one SM).
 //
 // Longest paths are computed WORK-EFFICIENTLY (O(n) node updates instead of the reference's O(n * depth)
 // Jacobi sweeps, env/message_passing_evl.py:176-197): every lane "walks" one machine's processing
 // sequence.  Its machine predecessor's value is in a register; only the job neighbour is read from
 // shared memory (sentinel -1 = not final yet).  One operation per lane per level => the number of
-// iterations equals the hop depth of the graph (27..210 at the reference's sizes) and each iteration
-// costs ~20 warp instructions regardless of n.  With n_m <= 16 the forward sweep (heads, lanes 0-15)
-// and the backward sweep (tails q, lanes 16-31) run in the SAME iterations.
+// iterations equals the hop depth of the graph (27..210 at the reference's sizes) and each iteration is a
+// couple of dozen warp instructions regardless of n.  With n_m <= 16 the forward sweep (lanes 0-15) and the
+// backward sweep (tails q, lanes 16-31) run in the SAME iterations.
+//
+// State format ("walk words"): the processing order of machine m is the row walk[m*n_j .. m*n_j+n_j) of
+// 32-bit words, one per operation:
+//     bits  0..15  node id (1..n)
+//     bits 16..27  duration (<= 4095)
+//     bit  28      first operation of its job   (job predecessor = S)
+//     bit  29      last operation of its job    (job successor = T)
+//     bit  30      "jobfirst": the job predecessor precedes the machine predecessor in networkx's
+//                  insertion order (set when a swap re-adds the machine in-edge)
+//     bit  31      last position of its machine row
+// so that one shared-memory load gives a walker everything about its next operation.  where[v] is the index
+// of node v's word.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace l2s {
 
-constexpr int kFirstFlag = 0x8000;  // node word: operation is the first of its job (job predecessor = S)
-constexpr int kLastFlag = 0x4000;   //            operation is the last of its job (job successor = T)
-constexpr int kDurMask = 0x3FFF;    //            duration (<= 16383)
+constexpr int kDurMax = 4095;
+// node words (uint16, indexed by node id, static): duration | flags
+constexpr int kFirstFlag = 0x8000;
+constexpr int kLastFlag = 0x4000;
+constexpr int kDurMask = 0x0FFF;
+// walk words
+constexpr unsigned kWId = 0xffffu;
+constexpr int kWDurShift = 16;
+constexpr unsigned kWFirst = 1u << 28;
+constexpr unsigned kWLast = 1u << 29;
+constexpr unsigned kWJf = 1u << 30;
+constexpr unsigned kWRowEnd = 1u << 31;
 constexpr unsigned kFull = 0xffffffffu;
+
+__host__ __device__ __forceinline__ unsigned make_walk(int v, int durw, bool jf, bool rowend) {
+  return (unsigned)v | ((unsigned)(durw & kDurMask) << kWDurShift) | ((durw & kFirstFlag) ? kWFirst : 0u) |
+         ((durw & kLastFlag) ? kWLast : 0u) | (jf ? kWJf : 0u) | (rowend ? kWRowEnd : 0u);
+}
 
 // Shapes and shared-memory layout of one instance (all offsets in bytes, 16-byte aligned).
 struct Layout {
   int n_j, n_m, n, n1;   // n = n_j*n_m operations, n1 = n+2 nodes
   int n1p;               // n1 rounded up to 4 (int32 elements per tq half)
-  int seq_stride;        // uint16 elements per instance in HBM/smem machine-order array (multiple of 8)
+  int walk_stride;       // uint32 words per instance (multiple of 4, >= n)
   int node_stride;       // uint16 elements per instance of node-indexed arrays (multiple of 8, >= n1)
   int mch_stride;        // bytes per instance of the machine-id array (multiple of 16)
-  int jf_words;          // uint32 words of tie-break history bits (multiple of 4)
   int e_mc;              // machine edges per instance n_m*(n_j-1)
-  int off_tq, off_seq, off_durw, off_crit, off_mch, off_jf, off_misc;
-  int bytes;             // per instance
+  int off_tq, off_walk, off_durw, off_crit;
+  int bytes;             // per instance (step kernel)
 };
-
-constexpr int kMiscInts = 8;
 
 // Persistent per-slice search state in HBM (SoA, one row per instance).
 struct State {
-  uint16_t* durw;   // [B][node_stride] node words (duration | flags), indexed by node id; 0 for S,T
-  uint8_t* mch;     // [B][mch_stride]  1-based machine of op v at [v-1]
-  uint16_t* seq;    // [B][seq_stride]  machine orders, row m at [m*n_j .. m*n_j+n_j)
-  uint32_t* jf;     // [B][jf_words]    bit v: job predecessor listed first (networkx insertion order)
+  uint32_t* walk;   // [B][walk_stride]  machine orders as walk words
+  uint16_t* where;  // [B][node_stride]  index of node v's walk word
+  uint16_t* durw;   // [B][node_stride]  node words (duration | flags), indexed by node id; 0 for S,T
+  uint8_t* mch;     // [B][mch_stride]   1-based machine of op v at [v-1] (setup/validation only)
   int32_t* tabu;    // [B][2]
   int32_t* cur;     // [B] current makespan
   int32_t* inc;     // [B] incumbent makespan
   int32_t* err;     // [1] first device-side error: (code<<24)|instance  (0 = none)
-  int32_t* est;     // [B][n1] last evaluation (test introspection)   -- may be null
-  int32_t* lst;     // [B][n1]
-  int32_t* path;    // [B][n] critical path (forward order)            -- may be null
-  int32_t* path_len;// [B]
 };
 
-struct Inst {            // shared-memory view of one instance
-  int32_t* tq;           // [2][n1p]: tq[v] = est[v]+dur[v] ("fin"), tq[n1p+v] = tail q[v]; -1 = pending
-  uint16_t* seq;
-  uint16_t* durw;
-  uint16_t* crit;        // chosen critical predecessor (networkx tie-break applied); 0 = S
-  uint8_t* mch;
-  uint32_t* jf;
-  int32_t* misc;
+// 32-bit shared-memory addressing (keeps the hot loops free of 64-bit generic pointer arithmetic)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return (int)v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, int v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+
+struct Inst {            // shared-memory view of one instance (32-bit shared addresses)
+  uint32_t tq;           // int32 [2][n1p]: [v] = est[v]+dur[v] ("fin"), [n1p+v] = tail q[v]; -1 = pending
+  uint32_t walk;         // uint32 [walk_stride]
+  uint32_t durw;         // uint16 [node_stride]
+  uint32_t crit;         // uint16 [node_stride] chosen critical predecessor (networkx tie-break); 0 = S
 };
 
-__device__ __forceinline__ Inst inst_view(const Layout& L, unsigned char* base) {
+__device__ __forceinline__ Inst inst_view(const Layout& L, uint32_t base) {
   Inst s;
-  s.tq = reinterpret_cast<int32_t*>(base + L.off_tq);
-  s.seq = reinterpret_cast<uint16_t*>(base + L.off_seq);
-  s.durw = reinterpret_cast<uint16_t*>(base + L.off_durw);
-  s.crit = reinterpret_cast<uint16_t*>(base + L.off_crit);
-  s.mch = reinterpret_cast<uint8_t*>(base + L.off_mch);
-  s.jf = reinterpret_cast<uint32_t*>(base + L.off_jf);
-  s.misc = reinterpret_cast<int32_t*>(base + L.off_misc);
+  s.tq = base + L.off_tq;
+  s.walk = base + L.off_walk;
+  s.durw = base + L.off_durw;
+  s.crit = base + L.off_crit;
   return s;
 }
 
 __device__ __forceinline__ void record_error(int32_t* err, int code, int b) {
-  // code is negative; keep the first one
-  atomicCAS(err, 0, (int)(((unsigned)(-code) << 24) | ((unsigned)b & 0xffffffu)));
+  atomicCAS(err, 0, (int)(((unsigned)(-code) << 24) | ((unsigned)b & 0xffffffu)));   // keep the first one
 }
 
 __device__ __forceinline__ uint4 ld_nc16(const void* p) {
@@ -86,92 +115,83 @@ __device__ __forceinline__ uint4 ld_nc16(const void* p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void fill_pending(const Layout& L, const Inst& s, int lane, bool fill_q) {
+  const uint4 pending = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  const int cnt = (fill_q ? 2 : 1) * (L.n1p / 4);
+  for (int i = lane; i < cnt; i += 32) sts128(s.tq + 16 * i, pending);
+}
 
 // Coalesced 16-byte staging of one instance's state into shared memory + sentinel fill of tq.
 __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, const State& st, int b, int lane,
                                                bool fill_q) {
   const uint4* gd = reinterpret_cast<const uint4*>(st.durw + (size_t)b * L.node_stride);
-  const uint4* gs = reinterpret_cast<const uint4*>(st.seq + (size_t)b * L.seq_stride);
-  const uint4* gm = reinterpret_cast<const uint4*>(st.mch + (size_t)b * L.mch_stride);
-  const uint4* gj = reinterpret_cast<const uint4*>(st.jf + (size_t)b * L.jf_words);
-  uint4* sd = reinterpret_cast<uint4*>(s.durw);
-  uint4* ss = reinterpret_cast<uint4*>(s.seq);
-  uint4* sm = reinterpret_cast<uint4*>(s.mch);
-  uint4* sj = reinterpret_cast<uint4*>(s.jf);
-  for (int i = lane; i < L.node_stride / 8; i += 32) sd[i] = ld_nc16(gd + i);   // static for the whole search
-  for (int i = lane; i < L.mch_stride / 16; i += 32) sm[i] = ld_nc16(gm + i);
-  for (int i = lane; i < L.seq_stride / 8; i += 32) ss[i] = gs[i];
-  for (int i = lane; i < L.jf_words / 4; i += 32) sj[i] = gj[i];
-  const int4 pending = make_int4(-1, -1, -1, -1);
-  int4* t4 = reinterpret_cast<int4*>(s.tq);
-  const int cnt = (fill_q ? 2 : 1) * (L.n1p / 4);
-  for (int i = lane; i < cnt; i += 32) t4[i] = pending;
-}
-
-__device__ __forceinline__ void fill_pending(const Layout& L, const Inst& s, int lane, bool fill_q) {
-  const int4 pending = make_int4(-1, -1, -1, -1);
-  int4* t4 = reinterpret_cast<int4*>(s.tq);
-  const int cnt = (fill_q ? 2 : 1) * (L.n1p / 4);
-  for (int i = lane; i < cnt; i += 32) t4[i] = pending;
+  const uint4* gw = reinterpret_cast<const uint4*>(st.walk + (size_t)b * L.walk_stride);
+  for (int i = lane; i < L.node_stride / 8; i += 32) sts128(s.durw + 16 * i, ld_nc16(gd + i));   // static
+  for (int i = lane; i < L.walk_stride / 4; i += 32) sts128(s.walk + 16 * i, gw[i]);
+  fill_pending(L, s, lane, fill_q);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Level-synchronous wavefront.  Lane role: machine `m` (row of seq), direction dir (0: forward est/fin
-// from the head of the row, 1: backward tail q from the end of the row), `active` lanes only.
-// Returns false if the selection is cyclic (no lane can advance).  `last` = final value of this lane's
+// Level-synchronous wavefront.  Lane role: machine row `m`, direction dir (0: forward est/fin from the head
+// of the row, 1: backward tail q from the end of the row); inactive lanes just vote.
+// Returns false if the selection is cyclic (no progress possible).  `last` = final value of the lane's
 // chain (forward: completion time of the machine's last operation).
-// kCrit: also record the critical predecessor of every operation (forward lanes).
+// kCrit: forward lanes also record the critical predecessor of every operation.
 // ------------------------------------------------------------------------------------------------------
 template <bool kCrit>
 __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m, int dir, bool active, int& last) {
-  volatile int32_t* tq = s.tq;
   const int n_j = L.n_j;
-  const int base = dir ? L.n1p : 0;
-  const int nbr = dir ? 1 : -1;
-  const int bflag = dir ? kLastFlag : kFirstFlag;
-  const int row = m * n_j;
-  int k = 0, prevval = 0, prevop = 0, cur = 0, dw = 0;
-  bool more = active;
-  if (more) {
-    cur = s.seq[row + (dir ? n_j - 1 : 0)];
-    dw = s.durw[cur];
-  }
-  int budget = L.n + 2;  // a DAG needs at most n levels
-  while (true) {
-    if (more) {
-      int nb = tq[base + cur + nbr];
-      nb = (dw & bflag) ? 0 : nb;
-      if (nb >= 0) {
-        const int val = max(prevval, nb) + (dw & kDurMask);
-        if (kCrit && !dir) {
-          const int jp = cur - 1;
-          int c;
-          if (dw & kFirstFlag) c = prevop;                        // machine predecessor, else S (=0)
-          else if (prevop == 0 || nb > prevval) c = jp;
-          else if (prevval > nb) c = prevop;
-          else c = (((s.jf[cur >> 5] >> (cur & 31)) & 1u) || jp < prevop) ? jp : prevop;  // tie: insertion order
-          s.crit[cur] = (uint16_t)c;
-        }
-        tq[base + cur] = val;
-        prevval = val;
-        prevop = cur;
-        ++k;
-        more = k < n_j;
-        if (more) {
-          cur = s.seq[row + (dir ? n_j - 1 - k : k)];
-          dw = s.durw[cur];
-        }
-      }
-    }
+  const uint32_t a_self = s.tq + (dir ? 4u * L.n1p : 0u);            // &tq[base + 0]
+  const uint32_t a_nb = dir ? a_self + 4u : a_self - 4u;             // &tq[base +- 1]
+  const unsigned bflag = dir ? kWLast : kWFirst;
+  const int stepb = dir ? -4 : 4;                                    // walk index step in bytes
+  uint32_t a_w = s.walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 : 0));
+  int left = active ? n_j : 0;                                       // operations still to place
+  int prevval = 0;
+  unsigned prevop = 0;
+  unsigned w = 0, wn = 0;
+  if (left > 0) w = (unsigned)lds32(a_w);
+  if (left > 1) wn = (unsigned)lds32(a_w + stepb);
+  int budget = (L.n + 3) >> 1;  // a DAG needs at most n levels; two levels per trip
+  const bool fwd_crit = kCrit && !dir;
+  // One level: place the lane's next operation if its job neighbour is final.  Straight-line (predicated)
+  // code: the warp stays converged, so shared-memory writes of one level are visible to the next.
+  auto level = [&]() {
+    const unsigned v = w & kWId;
+    int nb = -1;
+    if (left > 0) nb = lds32(a_nb + 4u * v);     // finished / inactive lanes must not touch memory
+    nb = (w & bflag) ? 0 : nb;
+    const bool adv = (left > 0) & (nb >= 0);
+    const int val = max(prevval, nb) + (int)((w >> kWDurShift) & (unsigned)kDurMask);
+    // first predecessor in networkx insertion order that attains the maximum (S only if none exists)
+    const unsigned jp = v - 1u;
+    const bool take_jp = (!(w & kWFirst)) & ((prevop == 0u) | (nb > prevval) |
+                                             ((nb == prevval) & (((w & kWJf) != 0u) | (jp < prevop))));
+    if (adv) sts32(a_self + 4u * v, val);
+    if (adv & fwd_crit) sts16(s.crit + 2u * v, (int)(take_jp ? jp : prevop));
+    prevval = adv ? val : prevval;
+    prevop = adv ? v : prevop;
+    w = adv ? wn : w;
+    a_w += adv ? stepb : 0;
+    left -= adv ? 1 : 0;
+    if (adv & (left > 1)) wn = (unsigned)lds32(a_w + stepb);
     __syncwarp();
-    if (!__any_sync(kFull, more)) break;
+  };
+  while (true) {
+    level();
+    level();
+    if (!__any_sync(kFull, left > 0)) break;
     if (--budget < 0) { last = prevval; return false; }
   }
   last = prevval;
   return true;
 }
 
-// Forward+backward evaluation by one warp.  Returns makespan, or -1 for a cyclic selection.
+// Forward (+ backward) evaluation by one warp.  Returns makespan, or -1 for a cyclic selection.
 // need_q: also compute the tails (latest start times).
 template <bool kCrit>
 __device__ __forceinline__ int evaluate_instance(const Layout& L, const Inst& s, int lane, bool need_q) {
@@ -194,53 +214,45 @@ __device__ __forceinline__ int evaluate_instance(const Layout& L, const Inst& s,
   return ok ? ms : -1;
 }
 
-// Swap the adjacent machine pair a0 -> a1 in shared memory (JsspN5.change_nxgraph_topology,
-// env/environment.py:318-354) and record the tie-break history bits.  Returns 0, 1 (dummy) or a negative
-// status; on error nothing is modified.  `pos_out` = position of a0 before the swap, `m_out` its machine.
-__device__ __forceinline__ int apply_swap(const Layout& L, const Inst& s, int a0, int a1, int lane, int& m_out,
-                                          int& pos_out, int& t_out) {
+// Swap the adjacent machine pair a0 -> a1 (JsspN5.change_nxgraph_topology, env/environment.py:318-354) in the
+// shared-memory walk array and set the tie-break history bits of a0, a1 and a1's old machine successor.
+// i0 = where[a0] (caller supplies it).  Returns 0, 1 (dummy) or -4 (not an adjacent pair on one machine); on
+// error nothing is modified.  Uniform across the warp; lane 0 writes.
+__device__ __forceinline__ int apply_swap(const Layout& L, const Inst& s, int a0, int a1, int i0, int lane,
+                                          bool& has_t) {
   if (a0 == 0 && a1 == 0) return 1;
-  if (a0 < 1 || a0 > L.n || a1 < 1 || a1 > L.n || a0 == a1) return -4;
-  const int m = (int)s.mch[a0 - 1] - 1;
-  if ((int)s.mch[a1 - 1] - 1 != m || m < 0 || m >= L.n_m) return -4;
-  uint16_t* row = s.seq + m * L.n_j;
-  int p = -1;
-  for (int k0 = 0; k0 < L.n_j; k0 += 32) {
-    const int k = k0 + lane;
-    const unsigned hit = __ballot_sync(kFull, k < L.n_j && row[k] == a0);
-    if (hit) { p = k0 + __ffs(hit) - 1; break; }
-  }
-  if (p < 0 || p + 1 >= L.n_j || row[p + 1] != a1) return -4;
-  const int t = (p + 2 < L.n_j) ? row[p + 2] : 0;
+  if (a0 < 1 || a0 > L.n || a1 < 1 || a1 > L.n || a0 == a1 || i0 < 0 || i0 >= L.n) return -4;
+  const unsigned w0 = (unsigned)lds32(s.walk + 4u * i0);
+  if ((int)(w0 & kWId) != a0 || (w0 & kWRowEnd)) return -4;
+  const unsigned w1 = (unsigned)lds32(s.walk + 4u * (i0 + 1));
+  if ((int)(w1 & kWId) != a1) return -4;
+  has_t = !(w1 & kWRowEnd);
   __syncwarp();
   if (lane == 0) {
-    row[p] = (uint16_t)a1;
-    row[p + 1] = (uint16_t)a0;
-    s.jf[a0 >> 5] |= 1u << (a0 & 31);
-    s.jf[a1 >> 5] |= 1u << (a1 & 31);
-    if (t) s.jf[t >> 5] |= 1u << (t & 31);
+    sts32(s.walk + 4u * i0, (int)((w1 & ~kWRowEnd) | kWJf));
+    sts32(s.walk + 4u * (i0 + 1), (int)((w0 & ~kWRowEnd) | kWJf | (w1 & kWRowEnd)));
+    if (has_t) sts32(s.walk + 4u * (i0 + 2), (int)((unsigned)lds32(s.walk + 4u * (i0 + 2)) | kWJf));
   }
   __syncwarp();
-  m_out = m; pos_out = p; t_out = t;
   return 0;
 }
 
 // Critical path == nx.dag_longest_path(G)[1:-1] (env/environment.py:77) by chasing the recorded critical
-// predecessors from T.  Written REVERSED (rp[0] = op next to T) as uint16 into `rp`.  Returns its length.
-__device__ __forceinline__ int trace_path(const Layout& L, const Inst& s, int ms, int lane, uint16_t* rp) {
+// predecessors from T.  Written REVERSED (rp[0] = op next to T) as uint16 at shared address `rp`.
+__device__ __forceinline__ int trace_path(const Layout& L, const Inst& s, int ms, int lane, uint32_t rp) {
   // T lists the job-last operations by ascending job: the first one that attains the makespan wins
   int start = 0;
   for (int j0 = 0; j0 < L.n_j; j0 += 32) {
     const int j = j0 + lane;
-    const unsigned hit = __ballot_sync(kFull, j < L.n_j && s.tq[j * L.n_m + L.n_m] == ms);
+    const unsigned hit = __ballot_sync(kFull, j < L.n_j && lds32(s.tq + 4u * (j * L.n_m + L.n_m)) == ms);
     if (hit) { start = (j0 + __ffs(hit) - 1) * L.n_m + L.n_m; break; }
   }
   int len = 0;
   int v = start;
   while (v != 0 && len < L.n) {   // uniform across the warp (broadcast loads)
-    if (lane == 0) rp[len] = (uint16_t)v;
+    if (lane == 0) sts16(rp + 2u * len, v);
     ++len;
-    v = s.crit[v];
+    v = lds16(s.crit + 2u * v);
   }
   __syncwarp();
   return len;
@@ -251,15 +263,15 @@ __device__ __forceinline__ int trace_path(const Layout& L, const Inst& s, int ms
 // emit(idx, a0, a1) is called by the owning lane for pair number idx; returns the pair count, or a negative
 // status (-9: the reference's IndexError corner).
 template <typename Emit>
-__device__ __forceinline__ int n5_moves(const Layout& L, const Inst& s, const uint16_t* rp, int len, int tabu0,
-                                        int tabu1, int lane, Emit emit) {
+__device__ __forceinline__ int n5_moves(const Layout& L, const Inst& s, uint32_t rp, int len, int tabu0, int tabu1,
+                                        int lane, Emit emit) {
   const int rg = len - 1;
   int count = 0;
   int err = 0;
-  auto pf = [&](int i) -> int { return rp[len - 1 - i]; };
+  auto pf = [&](int i) -> int { return lds16(rp + 2u * (len - 1 - i)); };
   auto same = [&](int i) -> bool {   // ops i and i+1 of the path share a machine (0 <= i < rg)
     const int u = pf(i), w = pf(i + 1);
-    return !(u == w - 1 && !(s.durw[w] & kFirstFlag));
+    return !(u == w - 1 && !(lds16(s.durw + 2u * w) & kFirstFlag));
   };
   for (int i0 = 0; i0 < rg; i0 += 32) {
     const int i = i0 + lane;

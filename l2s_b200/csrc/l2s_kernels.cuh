@@ -9,7 +9,7 @@ namespace l2s {
 // setup kernels (one warp per instance; not on the hot path)
 // ------------------------------------------------------------------------------------------------------
 
-// int32 durations / machine ids -> packed node words + byte machine ids, with input validation.
+// int32 durations / machine ids -> node words + byte machine ids, with input validation.
 __global__ void load_kernel(Layout L, State st, int B, const int32_t* __restrict__ dur,
                             const int32_t* __restrict__ mch) {
   const int lane = threadIdx.x & 31;
@@ -21,7 +21,7 @@ __global__ void load_kernel(Layout L, State st, int B, const int32_t* __restrict
     int word = 0;
     if (v >= 1 && v <= L.n) {
       const int d = dur[(size_t)b * L.n + v - 1];
-      if (d < 1 || d > kDurMask) bad |= 1;
+      if (d < 1 || d > kDurMax) bad |= 1;
       const int pos = (v - 1) % L.n_m;
       word = (d & kDurMask) | (pos == 0 ? kFirstFlag : 0) | (pos == L.n_m - 1 ? kLastFlag : 0);
       sum += d;
@@ -48,8 +48,7 @@ __global__ void load_kernel(Layout L, State st, int B, const int32_t* __restrict
   if (bad && lane == 0) record_error(st.err, (bad & 2) ? -7 : -6, b);
 }
 
-__device__ __forceinline__ void reset_dynamic(const Layout& L, const State& st, int b, int lane) {
-  for (int i = lane; i < L.jf_words; i += 32) st.jf[(size_t)b * L.jf_words + i] = 0;
+__device__ __forceinline__ void reset_dynamic(const State& st, int b, int lane) {
   if (lane == 0) {
     st.tabu[2 * b] = 0;
     st.tabu[2 * b + 1] = 0;
@@ -58,13 +57,15 @@ __device__ __forceinline__ void reset_dynamic(const Layout& L, const State& st, 
   }
 }
 
-// mseq [B, n_m, n_j] int32 node ids -> uint16 machine orders; validates rows.
+// mseq [B, n_m, n_j] int32 node ids -> walk words + where index; validates rows.
 __global__ void set_solution_kernel(Layout L, State st, int B, const int32_t* __restrict__ mseq) {
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
-  uint32_t* seen = st.jf + (size_t)b * L.jf_words;
-  for (int i = lane; i < L.jf_words; i += 32) seen[i] = 0;
+  uint16_t* where = st.where + (size_t)b * L.node_stride;
+  const uint16_t* durw = st.durw + (size_t)b * L.node_stride;
+  uint32_t* walk = st.walk + (size_t)b * L.walk_stride;
+  for (int i = lane; i < L.node_stride; i += 32) where[i] = 0xffff;
   __syncwarp();
   int bad = 0;
   for (int m = 0; m < L.n_m; ++m) {
@@ -75,15 +76,15 @@ __global__ void set_solution_kernel(Layout L, State st, int B, const int32_t* __
         bad = 1;
         v = 1;
       } else {
-        const unsigned old = atomicOr(&seen[v >> 5], 1u << (v & 31));
-        if (old & (1u << (v & 31))) bad = 1;
+        const unsigned short old = atomicCAS(reinterpret_cast<unsigned short*>(&where[v]), (unsigned short)0xffff,
+                                             (unsigned short)idx);
+        if (old != 0xffff) bad = 1;
       }
-      st.seq[(size_t)b * L.seq_stride + idx] = (uint16_t)v;
+      walk[idx] = make_walk(v, durw[v], false, k == L.n_j - 1);
     }
   }
-  for (int i = L.n + lane; i < L.seq_stride; i += 32) st.seq[(size_t)b * L.seq_stride + i] = 0;
-  __syncwarp();
-  reset_dynamic(L, st, b, lane);
+  for (int i = L.n + lane; i < L.walk_stride; i += 32) walk[i] = 0;
+  reset_dynamic(st, b, lane);
   bad = __reduce_or_sync(kFull, bad);
   if (bad && lane == 0) record_error(st.err, -10, b);
 }
@@ -92,7 +93,7 @@ __global__ void get_solution_kernel(Layout L, State st, int B, int32_t* __restri
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
-  for (int i = lane; i < L.n; i += 32) mseq[(size_t)b * L.n + i] = st.seq[(size_t)b * L.seq_stride + i];
+  for (int i = lane; i < L.n; i += 32) mseq[(size_t)b * L.n + i] = (int)(st.walk[(size_t)b * L.walk_stride + i] & kWId);
 }
 
 __global__ void export_misc_kernel(Layout L, State st, int B, uint8_t* jobfirst, float* makespan, float* incumbent) {
@@ -100,8 +101,12 @@ __global__ void export_misc_kernel(Layout L, State st, int B, uint8_t* jobfirst,
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
   if (jobfirst)
-    for (int v = lane; v < L.n1; v += 32)
-      jobfirst[(size_t)b * L.n1 + v] = (st.jf[(size_t)b * L.jf_words + (v >> 5)] >> (v & 31)) & 1u;
+    for (int v = lane; v < L.n1; v += 32) {
+      uint8_t bit = 0;
+      if (v >= 1 && v <= L.n)
+        bit = (st.walk[(size_t)b * L.walk_stride + st.where[(size_t)b * L.node_stride + v]] & kWJf) ? 1 : 0;
+      jobfirst[(size_t)b * L.n1 + v] = bit;
+    }
   if (lane == 0) {
     if (makespan) makespan[b] = (float)st.cur[b];
     if (incumbent) incumbent[b] = (float)st.inc[b];
@@ -238,8 +243,16 @@ __global__ void build_initial_kernel(Layout L, InitLayout IL, State st, int B, i
     }
     __syncwarp();
   }
-  for (int i = lane; i < L.seq_stride; i += 32) st.seq[(size_t)b * L.seq_stride + i] = i < L.n ? ops[i] : 0;
-  reset_dynamic(L, st, b, lane);
+  uint32_t* walk = st.walk + (size_t)b * L.walk_stride;
+  uint16_t* where = st.where + (size_t)b * L.node_stride;
+  for (int m = 0; m < n_m; ++m)
+    for (int k = lane; k < n_j; k += 32) {
+      const int idx = m * n_j + k, v = ops[idx];
+      walk[idx] = make_walk(v, durw[v], false, k == n_j - 1);
+      where[v] = (uint16_t)idx;
+    }
+  for (int i = L.n + lane; i < L.walk_stride; i += 32) walk[i] = 0;
+  reset_dynamic(st, b, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -281,13 +294,15 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
   const int b = blockIdx.x * (blockDim.x >> 5) + w;
   if (b >= a.B) return;
   const Layout& L = a.L;
-  const Inst s = inst_view(L, smem_step + (size_t)w * L.bytes);
+  const Inst s = inst_view(L, smem_addr(smem_step) + (uint32_t)w * (uint32_t)L.bytes);
   const int n = L.n, n1 = L.n1;
+  const uint16_t* gwhere = a.st.where + (size_t)b * L.node_stride;
 
-  int a0 = 0, a1 = 0;
+  int a0 = 0, a1 = 0, i0 = -1;
   if (a.actions && !a.export_only) {
     a0 = a.actions[2 * b];
     a1 = a.actions[2 * b + 1];
+    if (a0 >= 1 && a0 <= n) i0 = gwhere[a0];
   }
   int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
   const int inc_old = a.st.inc[b], cur_old = a.st.cur[b];
@@ -297,22 +312,23 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
   int status = 0;
   // 1. N5 swap (change_nxgraph_topology :318-354) + tabu update (:370-380)
   {
-    int m, p, t;
-    const int r = apply_swap(L, s, a0, a1, lane, m, p, t);
+    bool has_t = false;
+    const int r = apply_swap(L, s, a0, a1, i0, lane, has_t);
     if (r == 0) {
       tabu0 = a1;
       tabu1 = a0;
       if (lane == 0) {
-        uint16_t* grow = a.st.seq + (size_t)b * L.seq_stride + m * L.n_j;
-        grow[p] = (uint16_t)a1;
-        grow[p + 1] = (uint16_t)a0;
-        uint32_t* gj = a.st.jf + (size_t)b * L.jf_words;
-        gj[a0 >> 5] = s.jf[a0 >> 5];
-        gj[a1 >> 5] = s.jf[a1 >> 5];
-        if (t) gj[t >> 5] = s.jf[t >> 5];
+        uint32_t* gw = a.st.walk + (size_t)b * L.walk_stride;
+        gw[i0] = (uint32_t)lds32(s.walk + 4u * i0);
+        gw[i0 + 1] = (uint32_t)lds32(s.walk + 4u * (i0 + 1));
+        if (has_t) gw[i0 + 2] = (uint32_t)lds32(s.walk + 4u * (i0 + 2));
+        uint16_t* gwh = a.st.where + (size_t)b * L.node_stride;
+        gwh[a0] = (uint16_t)(i0 + 1);
+        gwh[a1] = (uint16_t)i0;
         a.st.tabu[2 * b] = tabu0;
         a.st.tabu[2 * b + 1] = tabu1;
       }
+      __syncwarp();
     } else if (r < 0) {
       status = r;
     }
@@ -331,53 +347,53 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
     }
     return;
   }
-  const int32_t* fin = s.tq;
-  const int32_t* q = s.tq + L.n1p;
+  const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   // latest start of S = min over job-first ops (:195 on the S row)
   int qs = 0;
-  for (int j = lane; j < L.n_j; j += 32) qs = max(qs, q[j * L.n_m + 1]);
+  for (int j = lane; j < L.n_j; j += 32) qs = max(qs, lds32(q + 4u * (j * L.n_m + 1)));
   qs = __reduce_max_sync(kFull, qs);
-  const int lst_s = ms - qs;
+  // S and T rows: est[S]=0, lst[S]=ms-qs, est[T]=lst[T]=ms (their node words are 0)
+  if (lane == 0) {
+    sts32(fin, 0);
+    sts32(q, qs);
+    sts32(fin + 4u * (n + 1), ms);
+    sts32(q + 4u * (n + 1), 0);
+  }
+  __syncwarp();
 
   // 3. node features x = [dur/high, est/c, lst/c] (env/environment.py:312), IEEE-RN float32 divisions
   if (a.x) {
     float* xo = a.x + (size_t)b * n1 * 3;
-    for (int e = lane; e < 3 * n1; e += 32) {
-      const int i = e / 3, c = e - 3 * i;
-      const int d = s.durw[i] & kDurMask;
-      int num;
-      if (c == 0) num = d;
-      else if (i == 0) num = c == 1 ? 0 : lst_s;
-      else if (i == n1 - 1) num = ms;
-      else num = c == 1 ? fin[i] - d : ms - q[i];
-      xo[e] = __fdiv_rn((float)num, c == 0 ? a.high : a.fea);
+    for (int i = lane; i < n1; i += 32) {
+      const int d = lds16(s.durw + 2u * i) & kDurMask;
+      const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
+      xo[3 * i] = __fdiv_rn((float)d, a.high);
+      xo[3 * i + 1] = __fdiv_rn((float)(f - d), a.fea);
+      xo[3 * i + 2] = __fdiv_rn((float)(ms - t), a.fea);
     }
   }
   if (a.ex_est) {
     for (int i = lane; i < n1; i += 32) {
-      const int d = s.durw[i] & kDurMask;
-      a.ex_est[(size_t)b * n1 + i] = i == 0 ? 0 : (i == n1 - 1 ? ms : fin[i] - d);
-      a.ex_lst[(size_t)b * n1 + i] = i == 0 ? lst_s : (i == n1 - 1 ? ms : ms - q[i]);
+      const int d = lds16(s.durw + 2u * i) & kDurMask;
+      a.ex_est[(size_t)b * n1 + i] = lds32(fin + 4u * i) - d;
+      a.ex_lst[(size_t)b * n1 + i] = ms - lds32(q + 4u * i);
     }
   }
-  __syncwarp();
 
-  // 4. machine edges ascending by source (dag2pyg :300-305); q is dead now, reuse it as scratch
-  uint16_t* msu = reinterpret_cast<uint16_t*>(s.tq + L.n1p);   // [n1] machine successor per node
-  uint16_t* rp = msu + n1;                                      // [n] reversed critical path
+  // 4. machine edges ascending by source (dag2pyg :300-305): successor of v = next word of its row
   if (a.emc) {
-    for (int m = 0; m < L.n_m; ++m) {
-      const uint16_t* row = s.seq + m * L.n_j;
-      for (int k = lane; k < L.n_j; k += 32) msu[row[k]] = (k + 1 < L.n_j) ? row[k + 1] : 0;
-    }
-    __syncwarp();
     const long long off = (long long)b * n1;
     long long* src = reinterpret_cast<long long*>(a.emc) + (size_t)b * L.e_mc;
     long long* dst = src + (size_t)a.B * L.e_mc;
     int cnt = 0;
     for (int v0 = 1; v0 <= n; v0 += 32) {
       const int v = v0 + lane;
-      const int sc = v <= n ? msu[v] : 0;
+      int sc = 0;
+      if (v <= n) {
+        const int wi = (v == a0 && status == 0) ? i0 + 1 : ((v == a1 && status == 0) ? i0 : (int)gwhere[v]);
+        const unsigned ww = (unsigned)lds32(s.walk + 4u * wi);
+        if (!(ww & kWRowEnd)) sc = lds32(s.walk + 4u * (wi + 1)) & (int)kWId;
+      }
       const unsigned bal = __ballot_sync(kFull, sc != 0);
       if (sc) {
         const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
@@ -387,11 +403,13 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
       cnt += __popc(bal);
     }
   }
+  __syncwarp();
 
-  // 5. critical path (nx.dag_longest_path, :77) and N5 move set (_get_pairs :84-105)
+  // 5. critical path (nx.dag_longest_path, :77) and N5 move set (_get_pairs :84-105); q is dead: reuse it
+  const uint32_t rp = q;   // uint16 [n] reversed critical path
   const int len = trace_path(L, s, ms, lane, rp);
   if (a.ex_path) {
-    for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = rp[len - 1 - i];
+    for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = lds16(rp + 2u * (len - 1 - i));
     if (lane == 0) a.ex_path_len[b] = len;
   }
   int32_t* po = a.pairs ? a.pairs + (size_t)b * a.pmax * 2 : nullptr;
@@ -450,24 +468,10 @@ struct RunArgs {
   int log_steps[kMaxLog];
   float* inc_log;
   int pmax;
-  int off_plist;   // byte offset (within the instance's smem) of the uint16 pair list [pmax][2]
-  int stride;      // shared-memory bytes per instance (state + pair list)
+  int off_where;   // byte offsets (within the instance's smem) of the where index (uint16 [node_stride]) ...
+  int off_plist;   // ... and of the uint16 pair list [pmax][2]
+  int stride;      // shared-memory bytes per instance (state + where + pair list)
 };
-
-// locate the adjacent pair (a0,a1): machine row and position, or -1
-__device__ __forceinline__ bool locate_pair(const Layout& L, const Inst& s, int a0, int a1, int lane, int& m, int& p) {
-  if (a0 < 1 || a0 > L.n || a1 < 1 || a1 > L.n || a0 == a1) return false;
-  m = (int)s.mch[a0 - 1] - 1;
-  if ((int)s.mch[a1 - 1] - 1 != m) return false;
-  const uint16_t* row = s.seq + m * L.n_j;
-  p = -1;
-  for (int k0 = 0; k0 < L.n_j; k0 += 32) {
-    const int k = k0 + lane;
-    const unsigned hit = __ballot_sync(kFull, k < L.n_j && row[k] == a0);
-    if (hit) { p = k0 + __ffs(hit) - 1; break; }
-  }
-  return p >= 0 && p + 1 < L.n_j && row[p + 1] == a1;
-}
 
 __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_run[];
@@ -475,15 +479,19 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   const int b = blockIdx.x * (blockDim.x >> 5) + w;
   if (b >= a.B) return;
   const Layout& L = a.L;
-  unsigned char* base = smem_run + (size_t)w * a.stride;
+  const uint32_t base = smem_addr(smem_run) + (uint32_t)w * (uint32_t)a.stride;
   const Inst s = inst_view(L, base);
-  uint16_t* plist = reinterpret_cast<uint16_t*>(base + a.off_plist);
-  uint16_t* rp = reinterpret_cast<uint16_t*>(s.tq + L.n1p);   // backward half is unused here
+  const uint32_t swhere = base + a.off_where, plist = base + a.off_plist;
+  const uint32_t rp = s.tq + 4u * L.n1p;   // the backward half of tq is unused here
   const int pmax = a.pmax;
 
   int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
   int inc = a.st.inc[b], cur = a.st.cur[b];
   stage_instance(L, s, a.st, b, lane, false);
+  {
+    const uint4* gwh = reinterpret_cast<const uint4*>(a.st.where + (size_t)b * L.node_stride);
+    for (int i = lane; i < L.node_stride / 8; i += 32) sts128(swhere + 16 * i, gwh[i]);
+  }
   __syncwarp();
   int status = 0;
   int ms = evaluate_instance<true>(L, s, lane, false);
@@ -492,7 +500,7 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   auto enumerate = [&]() {
     const int len = trace_path(L, s, ms, lane, rp);
     int c = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
-      if (idx < pmax) { plist[2 * idx] = (uint16_t)u; plist[2 * idx + 1] = (uint16_t)v; }
+      if (idx < pmax) { sts16(plist + 4u * idx, u); sts16(plist + 4u * idx + 2u, v); }
     });
     if (c < 0) { status = status ? status : c; c = 0; }
     if (c > pmax) { status = status ? status : -8; c = pmax; }
@@ -515,27 +523,32 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
           // GREEDY: evaluate every neighbour, first minimum wins (conventional_baselines...:186-197)
           int best = 0x7fffffff;
           for (int i = 0; i < np; ++i) {
-            int m, p;
-            locate_pair(L, s, plist[2 * i], plist[2 * i + 1], lane, m, p);
-            uint16_t* row = s.seq + m * L.n_j;
+            const int p0 = lds16(swhere + 2u * lds16(plist + 4u * i));
+            const uint32_t aw = s.walk + 4u * p0;
+            const unsigned w0 = (unsigned)lds32(aw), w1 = (unsigned)lds32(aw + 4u);
             __syncwarp();
-            if (lane == 0) { const uint16_t t0 = row[p]; row[p] = row[p + 1]; row[p + 1] = t0; }
+            if (lane == 0) {   // trial swap (row-end bit stays with the position, history bits untouched)
+              sts32(aw, (int)(w1 & ~kWRowEnd));
+              sts32(aw + 4u, (int)((w0 & ~kWRowEnd) | (w1 & kWRowEnd)));
+            }
             fill_pending(L, s, lane, false);
             __syncwarp();
             const int nms = evaluate_instance<false>(L, s, lane, false);
-            if (lane == 0) { const uint16_t t0 = row[p]; row[p] = row[p + 1]; row[p + 1] = t0; }
+            if (lane == 0) { sts32(aw, (int)w0); sts32(aw + 4u, (int)w1); }
             __syncwarp();
             if (nms >= 0 && nms < best) { best = nms; pick = i; }
           }
         }
-        a0 = plist[2 * pick];
-        a1 = plist[2 * pick + 1];
+        a0 = lds16(plist + 4u * pick);
+        a1 = lds16(plist + 4u * pick + 2u);
       }
-      int m, p, t;
-      const int r = apply_swap(L, s, a0, a1, lane, m, p, t);
+      const int i0 = (a0 >= 1 && a0 <= L.n) ? lds16(swhere + 2u * a0) : -1;
+      bool has_t = false;
+      const int r = apply_swap(L, s, a0, a1, i0, lane, has_t);
       if (r == 0) {
         tabu0 = a1;
         tabu1 = a0;
+        if (lane == 0) { sts16(swhere + 2u * a0, i0 + 1); sts16(swhere + 2u * a1, i0); }
       } else if (r < 0) {
         status = r;
       }
@@ -562,11 +575,10 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   }
   // write the search state back
   __syncwarp();
-  uint4* gs = reinterpret_cast<uint4*>(a.st.seq + (size_t)b * L.seq_stride);
-  const uint4* ss = reinterpret_cast<const uint4*>(s.seq);
-  for (int i = lane; i < L.seq_stride / 8; i += 32) gs[i] = ss[i];
-  uint32_t* gj = a.st.jf + (size_t)b * L.jf_words;
-  for (int i = lane; i < L.jf_words; i += 32) gj[i] = s.jf[i];
+  uint32_t* gw = a.st.walk + (size_t)b * L.walk_stride;
+  for (int i = lane; i < L.walk_stride; i += 32) gw[i] = (uint32_t)lds32(s.walk + 4u * i);
+  uint16_t* gwh = a.st.where + (size_t)b * L.node_stride;
+  for (int i = lane; i < L.node_stride; i += 32) gwh[i] = (uint16_t)lds16(swhere + 2u * i);
   if (lane == 0) {
     a.st.tabu[2 * b] = tabu0;
     a.st.tabu[2 * b + 1] = tabu1;
