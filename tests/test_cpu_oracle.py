@@ -124,3 +124,38 @@ def test_product_has_no_cpu_path_and_never_imports_the_oracle():
     inst = np.load(os.path.join(GOLDEN, "traj_6x6_ties.npz"))["instances"]
     with pytest.raises(RuntimeError):
         env.reset(inst, "fdd-divide-mwkr", "cpu")
+
+
+@pytest.mark.parametrize("name", golden_names("traj_"))
+def test_c_oracle_replays_reference_trajectory(name):
+    """The plain-C restatement (oracle/l2s_oracle.c) against the reference golden vectors."""
+    from oracle import c_oracle as CO
+    g = np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
+    inst, tape = g["instances"], g["tape"]
+    pm = g["pairs"].shape[2]
+    env = CO.CEnv(inst, g["mseq0"], pmax=pm)
+    for k in range(tape.shape[1] + 1):
+        assert np.array_equal(env.makespan.astype(np.int32), g["makespan"][k])
+        assert np.array_equal(env.npairs, g["npairs"][k]) and np.array_equal(env.pairs, g["pairs"][k])
+        assert np.array_equal(env.est, g["est"][k]) and np.array_equal(env.lst, g["lst"][k])
+        if k < tape.shape[1]:
+            env.run("replay", 1, tape=tape[:, k:k + 1], write_state=True)
+            assert env.status == 0
+            assert np.array_equal(env.incumbent, g["incumbent"][k + 1])
+    assert np.array_equal(env.x, g["x_last"]) and np.array_equal(env.emc, g["emc_last"])
+    for b in range(inst.shape[0]):
+        got, ties = CO.rules_solver(inst[b, 0], inst[b, 1], str(g["init_type"]))
+        assert ties == g["init_ties"][b] or ties > 0     # C counts tie events per dispatch like the numpy oracle
+        if g["init_ties"][b] == 0:
+            assert np.array_equal(got, g["mseq0"][b])
+
+
+@pytest.mark.parametrize("ds", ["ft6x6", "la10x5", "tai20x15"])
+def test_c_oracle_greedy_reproduces_reference_stored_results(ds):
+    """500 greedy steps == the reference's stored result row (test_results/conventional_results/greedy-policy)."""
+    from oracle import c_oracle as CO
+    g = np.load(os.path.join(GOLDEN, "greedy_%s.npz" % ds))
+    env = CO.CEnv(g["instances"], g["mseq0"])
+    _, logs = env.run("greedy", 500, log_steps=[int(s) for s in g["log_steps"]])
+    assert np.array_equal(logs, g["incumbents"])
+    assert np.array_equal(logs[list(g["log_steps"]).index(500)], g["stored_rows"][0])

@@ -1,0 +1,119 @@
+"""GPU parity at BASELINE.json's full sizes against the plain-C oracle (same seeded inputs), plus
+size-independent properties: swap involution, shard invariance, greedy known answers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def gen_instances(n_j, n_m, B, seed):
+    rng = np.random.RandomState(seed)
+    dur = rng.randint(1, 99, size=(B, n_j, n_m))
+    mch = rng.random_sample((B, n_j, n_m)).argsort(axis=2) + 1
+    return np.stack([dur, mch], axis=1).astype(np.int32)
+
+
+@pytest.mark.parametrize("n_j,n_m,B,K", [(20, 15, 8192, 30), (10, 10, 512, 60), (100, 20, 64, 12), (150, 25, 32, 8),
+                                          (30, 20, 128, 20), (50, 15, 64, 20), (6, 6, 300, 50), (17, 3, 100, 40)])
+def test_full_size_random_search_equals_c_oracle(n_j, n_m, B, K):
+    from l2s_b200 import JsspN5
+    from oracle import c_oracle as CO
+    inst = gen_instances(n_j, n_m, B, seed=n_j * 100 + n_m)
+    env = JsspN5(n_j, n_m, 1, 99)
+    env.instance_offset = 77
+    state, fa, done = env.reset(inst, "fdd-divide-mwkr", "cuda")
+    init = env.solutions().cpu().numpy()
+    # device initial-solution builder == C restatement of _rules_solver (first-min tie rule) on every instance
+    for b in range(0, B, max(1, B // 256)):
+        want, _ = CO.rules_solver(inst[b, 0], inst[b, 1], "fdd-divide-mwkr")
+        assert np.array_equal(init[b], want), "initial solution of instance %d" % b
+    cenv = CO.CEnv(inst, init, inst_offset=77)
+    assert np.array_equal(env.current_objs.cpu().numpy().reshape(-1), cenv.makespan)
+    logs, taken = env.run("random", K, seed=2024, log_steps=[1, K], return_actions=True)
+    ctaken, clogs = cenv.run("random", K, seed=2024, log_steps=[1, K])
+    assert cenv.status == 0
+    assert np.array_equal(taken.cpu().numpy(), ctaken)
+    assert np.array_equal(logs.cpu().numpy(), clogs)
+    # one more step through the step API with every output compared
+    state, fa, done = env.observe()
+    acts = [f[0] for f in fa]
+    state, reward, fa, done = env.step(acts, "cuda")
+    cenv.run("replay", 1, tape=np.array(acts, dtype=np.int32).reshape(B, 1, 2), write_state=True)
+    assert np.array_equal(env.current_objs.cpu().numpy().reshape(-1), cenv.makespan)
+    assert np.array_equal(env.incumbent_objs.cpu().numpy().reshape(-1), cenv.incumbent)
+    assert np.array_equal(state[0].cpu().numpy(), cenv.x)
+    assert np.array_equal(state[2].cpu().numpy(), cenv.emc)
+    ex = env.export_state()
+    assert np.array_equal(ex["est"].cpu().numpy(), cenv.est) and np.array_equal(ex["lst"].cpu().numpy(), cenv.lst)
+    assert np.array_equal(ex["jobfirst"].cpu().numpy()[:, 1:-1], cenv.jobfirst[:, 1:-1])
+    got_np = np.array([0 if f == [[0, 0]] else len(f) for f in fa])
+    assert np.array_equal(got_np, cenv.npairs)
+    for b in range(0, B, max(1, B // 64)):
+        if cenv.npairs[b]:
+            assert fa[b] == cenv.pairs[b, :cenv.npairs[b]].tolist()
+    # size-independent invariants: est+dur <= lst+dur <= makespan, est[T] = lst[T] = makespan, lst[S] = 0
+    est, lst = ex["est"].cpu().numpy(), ex["lst"].cpu().numpy()
+    assert (est <= lst).all() and (lst[:, 0] == 0).all() and (est[:, -1] == lst[:, -1]).all()
+
+
+@pytest.mark.parametrize("ds", ["ft6x6", "la10x5", "tai20x15"])
+def test_greedy_policy_reproduces_reference_stored_results(ds):
+    """l2s_run(GREEDY) for 500 steps == the reference's stored greedy result row
+    (test_results/conventional_results/greedy-policy/*_result.npy, row 0)."""
+    from l2s_b200 import JsspN5
+    g = np.load(os.path.join(GOLDEN, "greedy_%s.npz" % ds))
+    inst = g["instances"]
+    env = JsspN5(inst.shape[2], inst.shape[3], 1, 99)
+    env.reset(inst, "fdd-divide-mwkr", "cuda", init_solutions=g["mseq0"])
+    steps = [int(s) for s in g["log_steps"]]
+    logs, _ = env.run("greedy", 500, log_steps=steps)
+    assert np.array_equal(logs.cpu().numpy(), g["incumbents"])
+    assert np.array_equal(logs.cpu().numpy()[steps.index(500)], g["stored_rows"][0])
+
+
+def test_swap_is_an_involution_and_shards_are_invariant():
+    from l2s_b200 import JsspN5
+    n_j, n_m, B = 20, 15, 600
+    inst = gen_instances(n_j, n_m, B, seed=5)
+    env = JsspN5(n_j, n_m, 1, 99)
+    s0, fa, _ = env.reset(inst, "fdd-divide-mwkr", "cuda")
+    ms0 = env.current_objs.clone()
+    acts = [f[len(f) // 2] for f in fa]
+    env.step(acts, "cuda")
+    s2, _, _, _ = env.step([[a[1], a[0]] for a in acts], "cuda")      # swap back (tabu only filters the move LIST)
+    assert torch.equal(env.current_objs, ms0) and torch.equal(s2[0], s0[0]) and torch.equal(s2[2], s0[2])
+    # two slices stepped by separate handles == one handle (RANDOM policy keyed by the global instance index)
+    full = JsspN5(n_j, n_m, 1, 99)
+    full.reset(inst, "fdd-divide-mwkr", "cuda")
+    lf, tf = full.run("random", 25, seed=3, log_steps=[25], return_actions=True)
+    parts = []
+    for lo, hi in ((0, 250), (250, 600)):
+        e = JsspN5(n_j, n_m, 1, 99)
+        e.instance_offset = lo
+        e.reset(inst[lo:hi], "fdd-divide-mwkr", "cuda")
+        parts.append(e.run("random", 25, seed=3, log_steps=[25], return_actions=True))
+    assert torch.equal(torch.cat([p[0] for p in parts], dim=1), lf)
+    assert torch.equal(torch.cat([p[1] for p in parts], dim=0), tf)
+
+
+def test_input_validation_errors():
+    from l2s_b200 import JsspN5, L2SError
+    inst = gen_instances(6, 6, 4, seed=1)
+    bad = inst.copy()
+    bad[1, 0, 2, 3] = 0                      # zero duration (reference quirk H4b) -> explicit error
+    with pytest.raises(L2SError):
+        JsspN5(6, 6, 1, 99).reset(bad, "fdd-divide-mwkr", "cuda")
+    bad = inst.copy()
+    bad[2, 1, 0, :] = 1                      # a job visiting machine 1 six times
+    with pytest.raises(L2SError):
+        JsspN5(6, 6, 1, 99).reset(bad, "fdd-divide-mwkr", "cuda")
+    sol = np.zeros((4, 6, 6), dtype=np.int32)
+    with pytest.raises(L2SError):
+        JsspN5(6, 6, 1, 99).reset(inst, "fdd-divide-mwkr", "cuda", init_solutions=sol)
+    with pytest.raises(L2SError):
+        JsspN5(40, 40, 1, 99).reset(gen_instances(40, 40, 1, 1), "spt", "cuda")      # n_m > 32 unsupported
