@@ -3,6 +3,7 @@
 #include "../../include/l2s_b200.h"
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -44,16 +45,18 @@ Layout make_layout(int n_j, int n_m) {
   L.off_tq = off;   off += 2 * L.n1p * 4;
   L.off_walk = off; off += L.walk_stride * 4;
   L.off_durw = off; off += L.node_stride * 2;
-  L.off_crit = off; off += L.node_stride * 2;
+  L.off_aux = off;  off += 2 * L.node_stride * 2;
+  L.off_misc = off; off += 16;
   L.bytes = ru(off, 16);
   return L;
 }
 
 // warps (= instances) per CTA that maximise resident warps per SM; 0 if one instance does not fit
-int pick_warps(size_t bytes_per_inst) {
+int pick_warps(size_t bytes_per_inst, int max_w = 16) {
   int best = 0, best_w = 0;
   const int cand[] = {1, 2, 4, 8, 16};
   for (int w : cand) {
+    if (w > max_w) break;
     const size_t need = (size_t)w * bytes_per_inst;
     if (need > kSmemPerCtaMax) continue;
     long long ctas = (long long)(kSmemPerSm / (need + kSmemCtaReserve));
@@ -63,6 +66,28 @@ int pick_warps(size_t bytes_per_inst) {
     if (warps > best) { best = (int)warps; best_w = w; }
   }
   return best_w;
+}
+
+// Smallest number of FMA residual corrections (1 or 2) after which x*r reproduces the IEEE quotient x/c for
+// EVERY integer numerator 0 <= x <= max_num (the only values the kernels ever divide), or 0 if neither does
+// (then the kernels fall back to __fdiv_rn).  Same operations as div_rn() on the device: fmaf is correctly
+// rounded on both sides.
+int verify_divisor(float c, float* r_out, int max_num) {
+  if (!(c > 0.f) || !(c < 1e30f)) { *r_out = 0.f; return 0; }
+  const float r = (float)(1.0 / (double)c);   // correctly rounded: double rounding cannot occur for a float c
+  *r_out = r;
+  for (int mode = 1; mode <= 2; ++mode) {
+    bool ok = true;
+    for (int n = 0; n <= max_num && ok; ++n) {
+      const float x = (float)n;
+      float q = x * r;
+      q = fmaf(fmaf(-c, q, x), r, q);
+      if (mode == 2) q = fmaf(fmaf(-c, q, x), r, q);
+      ok = (q == x / c);
+    }
+    if (ok) return mode;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -85,6 +110,9 @@ struct l2s_handle_s {
   unsigned char* h_pack;  // pinned
   size_t pack_bytes;
   size_t off_npairs, off_status, off_reward, off_ms, off_inc, off_done, off_pairs;
+  // divisors already verified for the FMA division (x features)
+  float div_c[2], div_r[2];
+  int div_mode[2];
 };
 
 extern "C" {
@@ -137,8 +165,8 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
     I.off_pri = off;    off += ru((long long)n_j * 8, 16);
     I.bytes = off;
   }
-  h->warps_step = pick_warps(L.bytes);
-  if (const char* e = getenv("L2S_WARPS_STEP")) { int v = atoi(e); if (v > 0 && (size_t)v * L.bytes <= kSmemPerCtaMax) h->warps_step = v; }
+  h->warps_step = pick_warps(L.bytes, 4);   // step_kernel is compiled with __launch_bounds__(128, 10)
+  if (const char* e = getenv("L2S_WARPS_STEP")) { int v = atoi(e); if (v > 0 && v <= 4 && (size_t)v * L.bytes <= kSmemPerCtaMax) h->warps_step = v; }
   h->warps_run = pick_warps(h->run_stride);
   h->warps_init = pick_warps(h->IL.bytes);
   if (!h->warps_step || !h->warps_run || !h->warps_init) { free(h); return L2S_ERR_UNSUPPORTED_SHAPE; }
@@ -266,6 +294,14 @@ static StepArgs step_args(l2s_handle h, const l2s_step_io* io) {
     a.actions = io->actions;
     a.high = io->high;
     a.fea = io->fea_norm_const;
+    // feature divisions: dur/high has numerators <= kDurMax, est|lst/fea numerators < 2^24
+    if (h->div_c[0] != io->high) { h->div_c[0] = io->high; h->div_mode[0] = verify_divisor(io->high, &h->div_r[0], kDurMax); }
+    if (h->div_c[1] != io->fea_norm_const) {
+      h->div_c[1] = io->fea_norm_const;
+      h->div_mode[1] = verify_divisor(io->fea_norm_const, &h->div_r[1], (1 << 24) - 1);
+    }
+    a.r_high = h->div_r[0]; a.div_high = h->div_mode[0];
+    a.r_fea = h->div_r[1];  a.div_fea = h->div_mode[1];
     a.reward_type = io->reward_type;
     a.is_reset = io->is_reset;
     a.x = io->x;

@@ -56,14 +56,14 @@ struct Layout {
   int node_stride;       // uint16 elements per instance of node-indexed arrays (multiple of 8, >= n1)
   int mch_stride;        // bytes per instance of the machine-id array (multiple of 16)
   int e_mc;              // machine edges per instance n_m*(n_j-1)
-  int off_tq, off_walk, off_durw, off_crit;
+  int off_tq, off_walk, off_durw, off_aux, off_misc;   // aux = uint16 [2][node_stride]: critical predecessor | machine successor
   int bytes;             // per instance (step kernel)
 };
 
 // Persistent per-slice search state in HBM (SoA, one row per instance).
 struct State {
   uint32_t* walk;   // [B][walk_stride]  machine orders as walk words
-  uint16_t* where;  // [B][node_stride]  index of node v's walk word
+  uint16_t* where;  // [B][node_stride]  scratch (duplicate detection in l2s_set_solution); kernels rebuild positions
   uint16_t* durw;   // [B][node_stride]  node words (duration | flags), indexed by node id; 0 for S,T
   uint8_t* mch;     // [B][mch_stride]   1-based machine of op v at [v-1] (setup/validation only)
   int32_t* tabu;    // [B][2]
@@ -94,6 +94,8 @@ struct Inst {            // shared-memory view of one instance (32-bit shared ad
   uint32_t walk;         // uint32 [walk_stride]
   uint32_t durw;         // uint16 [node_stride]
   uint32_t crit;         // uint16 [node_stride] chosen critical predecessor (networkx tie-break); 0 = S
+  uint32_t msu;          // uint16 [node_stride] machine successor of every node (0 = none), by the backward sweep
+  uint32_t misc;         // int32 [4] parked scalars
 };
 
 __device__ __forceinline__ Inst inst_view(const Layout& L, uint32_t base) {
@@ -101,7 +103,9 @@ __device__ __forceinline__ Inst inst_view(const Layout& L, uint32_t base) {
   s.tq = base + L.off_tq;
   s.walk = base + L.off_walk;
   s.durw = base + L.off_durw;
-  s.crit = base + L.off_crit;
+  s.crit = base + L.off_aux;
+  s.msu = s.crit + 2u * L.node_stride;
+  s.misc = base + L.off_misc;
   return s;
 }
 
@@ -140,41 +144,35 @@ __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, c
 // of the row, 1: backward tail q from the end of the row); inactive lanes just vote.
 // Returns false if the selection is cyclic (no progress possible).  `last` = final value of the lane's
 // chain (forward: completion time of the machine's last operation).
-// kCrit: forward lanes also record the critical predecessor of every operation.
+// The loop body is kept minimal (one shared load, one shared store, a handful of ALU ops per level): it is
+// the serial spine of the whole step.  Critical predecessors / machine successors are derived afterwards in
+// one data-parallel pass (link_pass).
 // ------------------------------------------------------------------------------------------------------
-template <bool kCrit>
 __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m, int dir, bool active, int& last) {
   const int n_j = L.n_j;
   const uint32_t a_self = s.tq + (dir ? 4u * L.n1p : 0u);            // &tq[base + 0]
   const uint32_t a_nb = dir ? a_self + 4u : a_self - 4u;             // &tq[base +- 1]
+  const int dself = dir ? -4 : 4;                                    // a_self - a_nb
   const unsigned bflag = dir ? kWLast : kWFirst;
   const int stepb = dir ? -4 : 4;                                    // walk index step in bytes
   uint32_t a_w = s.walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 : 0));
   int left = active ? n_j : 0;                                       // operations still to place
   int prevval = 0;
-  unsigned prevop = 0;
   unsigned w = 0, wn = 0;
   if (left > 0) w = (unsigned)lds32(a_w);
   if (left > 1) wn = (unsigned)lds32(a_w + stepb);
   int budget = (L.n + 3) >> 1;  // a DAG needs at most n levels; two levels per trip
-  const bool fwd_crit = kCrit && !dir;
   // One level: place the lane's next operation if its job neighbour is final.  Straight-line (predicated)
   // code: the warp stays converged, so shared-memory writes of one level are visible to the next.
   auto level = [&]() {
-    const unsigned v = w & kWId;
+    const uint32_t a = a_nb + 4u * (w & kWId);
     int nb = -1;
-    if (left > 0) nb = lds32(a_nb + 4u * v);     // finished / inactive lanes must not touch memory
+    if (left > 0) nb = lds32(a);                 // finished / inactive lanes must not touch memory
     nb = (w & bflag) ? 0 : nb;
     const bool adv = (left > 0) & (nb >= 0);
     const int val = max(prevval, nb) + (int)((w >> kWDurShift) & (unsigned)kDurMask);
-    // first predecessor in networkx insertion order that attains the maximum (S only if none exists)
-    const unsigned jp = v - 1u;
-    const bool take_jp = (!(w & kWFirst)) & ((prevop == 0u) | (nb > prevval) |
-                                             ((nb == prevval) & (((w & kWJf) != 0u) | (jp < prevop))));
-    if (adv) sts32(a_self + 4u * v, val);
-    if (adv & fwd_crit) sts16(s.crit + 2u * v, (int)(take_jp ? jp : prevop));
+    if (adv) sts32(a + dself, val);
     prevval = adv ? val : prevval;
-    prevop = adv ? v : prevop;
     w = adv ? wn : w;
     a_w += adv ? stepb : 0;
     left -= adv ? 1 : 0;
@@ -193,25 +191,48 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
 
 // Forward (+ backward) evaluation by one warp.  Returns makespan, or -1 for a cyclic selection.
 // need_q: also compute the tails (latest start times).
-template <bool kCrit>
 __device__ __forceinline__ int evaluate_instance(const Layout& L, const Inst& s, int lane, bool need_q) {
   int last = 0;
   bool ok;
   int fwd_last = 0;
   if (L.n_m <= 16 && need_q) {
     const int m = lane & 15, dir = lane >> 4;
-    ok = wavefront<kCrit>(L, s, m, dir, m < L.n_m, last);
+    ok = wavefront(L, s, m, dir, m < L.n_m, last);
     fwd_last = dir ? 0 : last;
   } else {
-    ok = wavefront<kCrit>(L, s, lane, 0, lane < L.n_m, last);
+    ok = wavefront(L, s, lane, 0, lane < L.n_m, last);
     fwd_last = last;
     if (need_q && ok) {
       int l2;
-      ok = wavefront<false>(L, s, lane, 1, lane < L.n_m, l2);
+      ok = wavefront(L, s, lane, 1, lane < L.n_m, l2);
     }
   }
   const int ms = __reduce_max_sync(kFull, fwd_last);
   return ok ? ms : -1;
+}
+
+// Data-parallel pass over the walk words after an evaluation: for every operation record
+//   crit[v] = its critical predecessor = the FIRST predecessor in networkx's G.pred[v] insertion order that
+//             attains est[v] (job predecessor listed first iff the jobfirst bit is set or jp < mp; S, = 0, only
+//             if there is no other predecessor) -- this is what nx.dag_longest_path keeps per node;
+//   msu[v]  = its machine successor (0 = none), if want_msu.
+__device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, int lane, bool want_msu) {
+  for (int i = lane; i < L.n; i += 32) {
+    const unsigned w = (unsigned)lds32(s.walk + 4u * i);
+    const unsigned wp = i > 0 ? (unsigned)lds32(s.walk + 4u * (i - 1)) : kWRowEnd;
+    const unsigned v = w & kWId;
+    const unsigned mp = (wp & kWRowEnd) ? 0u : (wp & kWId);       // row start <=> previous word ends a row
+    const unsigned jp = v - 1u;
+    const int fj = (w & kWFirst) ? -1 : lds32(s.tq + 4u * jp);     // completion of the job predecessor
+    const int fm = mp ? lds32(s.tq + 4u * mp) : -1;
+    const bool take_jp = (fj >= 0) & ((fm < 0) | (fj > fm) | ((fj == fm) & (((w & kWJf) != 0u) | (jp < mp))));
+    sts16(s.crit + 2u * v, (int)(take_jp ? jp : mp));
+    if (want_msu) {
+      const unsigned ms = (w & kWRowEnd) ? 0u : ((unsigned)lds32(s.walk + 4u * (i + 1)) & kWId);
+      sts16(s.msu + 2u * v, (int)ms);
+    }
+  }
+  __syncwarp();
 }
 
 // Swap the adjacent machine pair a0 -> a1 (JsspN5.change_nxgraph_topology, env/environment.py:318-354) in the

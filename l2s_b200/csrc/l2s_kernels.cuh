@@ -100,13 +100,13 @@ __global__ void export_misc_kernel(Layout L, State st, int B, uint8_t* jobfirst,
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
-  if (jobfirst)
-    for (int v = lane; v < L.n1; v += 32) {
-      uint8_t bit = 0;
-      if (v >= 1 && v <= L.n)
-        bit = (st.walk[(size_t)b * L.walk_stride + st.where[(size_t)b * L.node_stride + v]] & kWJf) ? 1 : 0;
-      jobfirst[(size_t)b * L.n1 + v] = bit;
+  if (jobfirst) {
+    if (lane == 0) { jobfirst[(size_t)b * L.n1] = 0; jobfirst[(size_t)b * L.n1 + L.n + 1] = 0; }
+    for (int i = lane; i < L.n; i += 32) {
+      const unsigned w = st.walk[(size_t)b * L.walk_stride + i];
+      jobfirst[(size_t)b * L.n1 + (w & kWId)] = (w & kWJf) ? 1 : 0;
     }
+  }
   if (lane == 0) {
     if (makespan) makespan[b] = (float)st.cur[b];
     if (incumbent) incumbent[b] = (float)st.inc[b];
@@ -244,12 +244,10 @@ __global__ void build_initial_kernel(Layout L, InitLayout IL, State st, int B, i
     __syncwarp();
   }
   uint32_t* walk = st.walk + (size_t)b * L.walk_stride;
-  uint16_t* where = st.where + (size_t)b * L.node_stride;
   for (int m = 0; m < n_m; ++m)
     for (int k = lane; k < n_j; k += 32) {
       const int idx = m * n_j + k, v = ops[idx];
       walk[idx] = make_walk(v, durw[v], false, k == n_j - 1);
-      where[v] = (uint16_t)idx;
     }
   for (int i = L.n + lane; i < L.walk_stride; i += 32) walk[i] = 0;
   reset_dynamic(st, b, lane);
@@ -258,12 +256,25 @@ __global__ void build_initial_kernel(Layout L, InitLayout IL, State st, int B, i
 // ------------------------------------------------------------------------------------------------------
 // The environment step: JsspN5.step (env/environment.py:356-387), one launch for the whole slice.
 // ------------------------------------------------------------------------------------------------------
+// IEEE round-to-nearest float32 quotient x/c for a launch-constant divisor.  mode 1/2: x*r with one/two
+// FMA residual corrections (r = correctly rounded 1/c); the host verified exhaustively over the numerator
+// range that this equals x/c bit for bit for THIS c (l2s_capi.cu: verify_divisor); mode 0: __fdiv_rn.
+__device__ __forceinline__ float div_rn(float x, float c, float r, int mode) {
+  if (mode == 0) return __fdiv_rn(x, c);
+  float q = __fmul_rn(x, r);
+  q = __fmaf_rn(__fmaf_rn(-c, q, x), r, q);
+  if (mode == 2) q = __fmaf_rn(__fmaf_rn(-c, q, x), r, q);
+  return q;
+}
+
 struct StepArgs {
   Layout L;
   State st;
   int B;
   const int32_t* actions;
   float high, fea;
+  float r_high, r_fea;     // correctly rounded reciprocals
+  int div_high, div_fea;   // 1/2: FMA-corrected reciprocal division verified bit-exact on the host, 0: __fdiv_rn
   int reward_type, is_reset;
   float* x;
   int64_t* emc;
@@ -288,7 +299,8 @@ struct StepArgs {
   int32_t* ex_path_len;
 };
 
-__global__ void step_kernel(const __grid_constant__ StepArgs a) {
+// <= 4 warps per CTA, >= 10 CTAs per SM: caps the kernel at 48 registers so that 40 instances stay resident
+__global__ void __launch_bounds__(128, 10) step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_step[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = blockIdx.x * (blockDim.x >> 5) + w;
@@ -296,18 +308,25 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
   const Layout& L = a.L;
   const Inst s = inst_view(L, smem_addr(smem_step) + (uint32_t)w * (uint32_t)L.bytes);
   const int n = L.n, n1 = L.n1;
-  const uint16_t* gwhere = a.st.where + (size_t)b * L.node_stride;
 
-  int a0 = 0, a1 = 0, i0 = -1;
+  int a0 = 0, a1 = 0;
   if (a.actions && !a.export_only) {
     a0 = a.actions[2 * b];
     a1 = a.actions[2 * b + 1];
-    if (a0 >= 1 && a0 <= n) i0 = gwhere[a0];
   }
   int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
-  const int inc_old = a.st.inc[b], cur_old = a.st.cur[b];
+  const int inc_in = a.st.inc[b], cur_in = a.st.cur[b];
   stage_instance(L, s, a.st, b, lane, true);
+  // park the scalars that are only needed at the very end in shared memory (registers are the occupancy limit)
+  if (lane == 0) { sts32(s.misc, inc_in); sts32(s.misc + 4u, cur_in); }
   __syncwarp();
+  // position of a0 in the machine orders: scan the staged walk words (no index array to keep in HBM)
+  int i0 = -1;
+  if (a0 >= 1 && a0 <= n) {
+    for (int i = lane; i < n; i += 32)
+      if ((lds32(s.walk + 4u * i) & (int)kWId) == a0) i0 = i;
+    i0 = __reduce_max_sync(kFull, i0);
+  }
 
   int status = 0;
   // 1. N5 swap (change_nxgraph_topology :318-354) + tabu update (:370-380)
@@ -322,9 +341,6 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
         gw[i0] = (uint32_t)lds32(s.walk + 4u * i0);
         gw[i0 + 1] = (uint32_t)lds32(s.walk + 4u * (i0 + 1));
         if (has_t) gw[i0 + 2] = (uint32_t)lds32(s.walk + 4u * (i0 + 2));
-        uint16_t* gwh = a.st.where + (size_t)b * L.node_stride;
-        gwh[a0] = (uint16_t)(i0 + 1);
-        gwh[a1] = (uint16_t)i0;
         a.st.tabu[2 * b] = tabu0;
         a.st.tabu[2 * b + 1] = tabu1;
       }
@@ -335,7 +351,7 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
   }
 
   // 2. evaluate (Evaluator.forward, env/message_passing_evl.py:161-199) + critical predecessors
-  const int ms = evaluate_instance<true>(L, s, lane, true);
+  const int ms = evaluate_instance(L, s, lane, true);
   if (ms < 0) {
     status = -5;
     if (lane == 0) {
@@ -347,6 +363,7 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
     }
     return;
   }
+  link_pass(L, s, lane, a.emc != nullptr);
   const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   // latest start of S = min over job-first ops (:195 on the S row)
   int qs = 0;
@@ -361,15 +378,16 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
   }
   __syncwarp();
 
-  // 3. node features x = [dur/high, est/c, lst/c] (env/environment.py:312), IEEE-RN float32 divisions
+  // 3. node features x = [dur/high, est/c, lst/c] (env/environment.py:312): float32 IEEE-RN quotients
   if (a.x) {
     float* xo = a.x + (size_t)b * n1 * 3;
+    const float fms = (float)ms;
     for (int i = lane; i < n1; i += 32) {
       const int d = lds16(s.durw + 2u * i) & kDurMask;
       const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
-      xo[3 * i] = __fdiv_rn((float)d, a.high);
-      xo[3 * i + 1] = __fdiv_rn((float)(f - d), a.fea);
-      xo[3 * i + 2] = __fdiv_rn((float)(ms - t), a.fea);
+      xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
+      xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
+      xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
     }
   }
   if (a.ex_est) {
@@ -380,7 +398,7 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
     }
   }
 
-  // 4. machine edges ascending by source (dag2pyg :300-305): successor of v = next word of its row
+  // 4. machine edges ascending by source (dag2pyg :300-305); successors were recorded by the backward sweep
   if (a.emc) {
     const long long off = (long long)b * n1;
     long long* src = reinterpret_cast<long long*>(a.emc) + (size_t)b * L.e_mc;
@@ -388,12 +406,7 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
     int cnt = 0;
     for (int v0 = 1; v0 <= n; v0 += 32) {
       const int v = v0 + lane;
-      int sc = 0;
-      if (v <= n) {
-        const int wi = (v == a0 && status == 0) ? i0 + 1 : ((v == a1 && status == 0) ? i0 : (int)gwhere[v]);
-        const unsigned ww = (unsigned)lds32(s.walk + 4u * wi);
-        if (!(ww & kWRowEnd)) sc = lds32(s.walk + 4u * (wi + 1)) & (int)kWId;
-      }
+      const int sc = v <= n ? lds16(s.msu + 2u * v) : 0;
       const unsigned bal = __ballot_sync(kFull, sc != 0);
       if (sc) {
         const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
@@ -425,6 +438,7 @@ __global__ void step_kernel(const __grid_constant__ StepArgs a) {
 
   // 6. reward / incumbent / current (:359-367)
   if (lane == 0) {
+    const int inc_old = lds32(s.misc), cur_old = lds32(s.misc + 4u);
     int reward, inc;
     if (a.is_reset) {
       reward = 0;
@@ -488,16 +502,15 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
   int inc = a.st.inc[b], cur = a.st.cur[b];
   stage_instance(L, s, a.st, b, lane, false);
-  {
-    const uint4* gwh = reinterpret_cast<const uint4*>(a.st.where + (size_t)b * L.node_stride);
-    for (int i = lane; i < L.node_stride / 8; i += 32) sts128(swhere + 16 * i, gwh[i]);
-  }
+  __syncwarp();
+  for (int i = lane; i < L.n; i += 32) sts16(swhere + 2u * (lds32(s.walk + 4u * i) & (int)kWId), i);
   __syncwarp();
   int status = 0;
-  int ms = evaluate_instance<true>(L, s, lane, false);
+  int ms = evaluate_instance(L, s, lane, false);
   if (ms < 0) status = -5;
   int np = 0;
   auto enumerate = [&]() {
+    link_pass(L, s, lane, false);
     const int len = trace_path(L, s, ms, lane, rp);
     int c = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
       if (idx < pmax) { sts16(plist + 4u * idx, u); sts16(plist + 4u * idx + 2u, v); }
@@ -533,7 +546,7 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
             }
             fill_pending(L, s, lane, false);
             __syncwarp();
-            const int nms = evaluate_instance<false>(L, s, lane, false);
+            const int nms = evaluate_instance(L, s, lane, false);
             if (lane == 0) { sts32(aw, (int)w0); sts32(aw + 4u, (int)w1); }
             __syncwarp();
             if (nms >= 0 && nms < best) { best = nms; pick = i; }
@@ -555,7 +568,7 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
       if (!status && r == 0) {   // a dummy move leaves the schedule, its makespan and its move set unchanged
         fill_pending(L, s, lane, false);
         __syncwarp();
-        ms = evaluate_instance<true>(L, s, lane, false);
+        ms = evaluate_instance(L, s, lane, false);
         if (ms < 0) status = -5;
       }
       if (!status && r == 0) {
@@ -577,8 +590,6 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   __syncwarp();
   uint32_t* gw = a.st.walk + (size_t)b * L.walk_stride;
   for (int i = lane; i < L.walk_stride; i += 32) gw[i] = (uint32_t)lds32(s.walk + 4u * i);
-  uint16_t* gwh = a.st.where + (size_t)b * L.node_stride;
-  for (int i = lane; i < L.node_stride; i += 32) gwh[i] = (uint16_t)lds16(swhere + 2u * i);
   if (lane == 0) {
     a.st.tabu[2 * b] = tabu0;
     a.st.tabu[2 * b + 1] = tabu1;
