@@ -140,6 +140,7 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   if (!out || n_j < 2 || n_m < 1 || batch < 1 || pmax < 0) return L2S_ERR_INVALID_ARG;
   if (pmax == 0) pmax = 32;
   if (n_m > 32 || (long long)n_j * n_m + 2 > 65535) return L2S_ERR_UNSUPPORTED_SHAPE;
+  if ((long long)batch * ((long long)n_j * n_m + 2) >= (1ll << 31)) return L2S_ERR_INVALID_ARG;   // 32-bit node ids per slice
   CU(cudaSetDevice(device));
   l2s_handle h = (l2s_handle)calloc(1, sizeof(l2s_handle_s));
   if (!h) return L2S_ERR_INVALID_ARG;

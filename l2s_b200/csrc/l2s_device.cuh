@@ -152,9 +152,8 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
   const int n_j = L.n_j;
   const uint32_t a_self = s.tq + (dir ? 4u * L.n1p : 0u);            // &tq[base + 0]
   const uint32_t a_nb = dir ? a_self + 4u : a_self - 4u;             // &tq[base +- 1]
-  const int dself = dir ? -4 : 4;                                    // a_self - a_nb
   const unsigned bflag = dir ? kWLast : kWFirst;
-  const int stepb = dir ? -4 : 4;                                    // walk index step in bytes
+  const int stepb = dir ? -4 : 4;                                    // walk step in bytes; also a_self - a_nb
   uint32_t a_w = s.walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 : 0));
   int left = active ? n_j : 0;                                       // operations still to place
   int prevval = 0;
@@ -165,18 +164,39 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
   // One level: place the lane's next operation if its job neighbour is final.  Straight-line (predicated)
   // code: the warp stays converged, so shared-memory writes of one level are visible to the next.
   auto level = [&]() {
-    const uint32_t a = a_nb + 4u * (w & kWId);
-    int nb = -1;
-    if (left > 0) nb = lds32(a);                 // finished / inactive lanes must not touch memory
-    nb = (w & bflag) ? 0 : nb;
-    const bool adv = (left > 0) & (nb >= 0);
-    const int val = max(prevval, nb) + (int)((w >> kWDurShift) & (unsigned)kDurMask);
-    if (adv) sts32(a + dself, val);
-    prevval = adv ? val : prevval;
-    w = adv ? wn : w;
-    a_w += adv ? stepb : 0;
-    left -= adv ? 1 : 0;
-    if (adv & (left > 1)) wn = (unsigned)lds32(a_w + stepb);
+    // Hand-scheduled: 21 instructions, fully predicated.  Equivalent C:
+    //   a = a_nb + 4*(w & 0xffff); nb = left > 0 ? tq[a] : -1; if (w & bflag) nb = 0;
+    //   adv = left > 0 && nb >= 0; val = max(prevval, nb) + dur(w);
+    //   if (adv) { tq[a + dself] = val; prevval = val; w = wn; a_w += stepb; --left; if (left > 1) wn = walk[a_w + stepb]; }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pa, pb, pv, pl;\n\t"
+        ".reg .b32 a, nb, t, d, val;\n\t"
+        "setp.gt.s32 pa, %2, 0;\n\t"
+        "and.b32 a, %0, 0xffff;\n\t"
+        "mad.lo.u32 a, a, 4, %5;\n\t"
+        "mov.b32 nb, -1;\n\t"
+        "@pa ld.shared.b32 nb, [a];\n\t"
+        "and.b32 t, %0, %6;\n\t"
+        "setp.ne.u32 pb, t, 0;\n\t"
+        "selp.b32 nb, 0, nb, pb;\n\t"
+        "setp.ge.and.s32 pv, nb, 0, pa;\n\t"
+        "bfe.u32 d, %0, 16, 12;\n\t"
+        "max.s32 val, %3, nb;\n\t"
+        "add.s32 val, val, d;\n\t"
+        "add.s32 a, a, %7;\n\t"
+        "@pv st.shared.b32 [a], val;\n\t"
+        "@pv mov.b32 %3, val;\n\t"
+        "@pv mov.b32 %0, %1;\n\t"
+        "@pv add.s32 %4, %4, %7;\n\t"
+        "@pv add.s32 %2, %2, -1;\n\t"
+        "setp.gt.and.s32 pl, %2, 1, pv;\n\t"
+        "add.s32 t, %4, %7;\n\t"
+        "@pl ld.shared.b32 %1, [t];\n\t"
+        "}\n"
+        : "+r"(w), "+r"(wn), "+r"(left), "+r"(prevval), "+r"(a_w)
+        : "r"(a_nb), "r"(bflag), "r"(stepb)
+        : "memory");
     __syncwarp();
   };
   while (true) {
@@ -216,7 +236,8 @@ __device__ __forceinline__ int evaluate_instance(const Layout& L, const Inst& s,
 //             attains est[v] (job predecessor listed first iff the jobfirst bit is set or jp < mp; S, = 0, only
 //             if there is no other predecessor) -- this is what nx.dag_longest_path keeps per node;
 //   msu[v]  = its machine successor (0 = none), if want_msu.
-__device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, int lane, bool want_msu) {
+template <bool want_msu>
+__device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, int lane) {
   for (int i = lane; i < L.n; i += 32) {
     const unsigned w = (unsigned)lds32(s.walk + 4u * i);
     const unsigned wp = i > 0 ? (unsigned)lds32(s.walk + 4u * (i - 1)) : kWRowEnd;

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128, 10) step_kernel(const __grid_constant__ S
     }
     return;
   }
-  link_pass(L, s, lane, a.emc != nullptr);
+  if (a.emc) link_pass<true>(L, s, lane); else link_pass<false>(L, s, lane);
   const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   // latest start of S = min over job-first ops (:195 on the S row)
   int qs = 0;
@@ -380,14 +380,27 @@ __global__ void __launch_bounds__(128, 10) step_kernel(const __grid_constant__ S
 
   // 3. node features x = [dur/high, est/c, lst/c] (env/environment.py:312): float32 IEEE-RN quotients
   if (a.x) {
-    float* xo = a.x + (size_t)b * n1 * 3;
+    float* xo = a.x + (size_t)b * n1 * 3 + 3 * lane;
     const float fms = (float)ms;
-    for (int i = lane; i < n1; i += 32) {
-      const int d = lds16(s.durw + 2u * i) & kDurMask;
-      const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
-      xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
-      xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
-      xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
+    if (a.div_high == 1 && a.div_fea == 1) {
+      // common case: one FMA residual correction reproduces the IEEE quotient (verified on the host)
+      const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
+      for (int i = lane; i < n1; i += 32, xo += 96) {
+        const int d = lds16(s.durw + 2u * i) & kDurMask;
+        const float fd = (float)d, fe = (float)(lds32(fin + 4u * i) - d), fl = fms - (float)lds32(q + 4u * i);
+        float q0 = __fmul_rn(fd, rh), q1 = __fmul_rn(fe, rf), q2 = __fmul_rn(fl, rf);
+        xo[0] = __fmaf_rn(__fmaf_rn(-ch, q0, fd), rh, q0);
+        xo[1] = __fmaf_rn(__fmaf_rn(-cf, q1, fe), rf, q1);
+        xo[2] = __fmaf_rn(__fmaf_rn(-cf, q2, fl), rf, q2);
+      }
+    } else {
+      for (int i = lane; i < n1; i += 32, xo += 96) {
+        const int d = lds16(s.durw + 2u * i) & kDurMask;
+        const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
+        xo[0] = div_rn((float)d, a.high, a.r_high, a.div_high);
+        xo[1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
+        xo[2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
+      }
     }
   }
   if (a.ex_est) {
@@ -398,22 +411,25 @@ __global__ void __launch_bounds__(128, 10) step_kernel(const __grid_constant__ S
     }
   }
 
-  // 4. machine edges ascending by source (dag2pyg :300-305); successors were recorded by the backward sweep
+  // 4. machine edges ascending by source (dag2pyg :300-305); successors were recorded by link_pass.
+  //    Node ids of a slice fit 32 bits (checked in l2s_create): 32-bit arithmetic, 64-bit stores.
   if (a.emc) {
-    const long long off = (long long)b * n1;
-    long long* src = reinterpret_cast<long long*>(a.emc) + (size_t)b * L.e_mc;
-    long long* dst = src + (size_t)a.B * L.e_mc;
-    int cnt = 0;
+    const unsigned off = (unsigned)b * (unsigned)n1;
+    uint2* src = reinterpret_cast<uint2*>(a.emc) + (size_t)b * L.e_mc;
+    uint2* dst = src + (size_t)a.B * L.e_mc;
+    const unsigned below = (1u << lane) - 1u;
     for (int v0 = 1; v0 <= n; v0 += 32) {
       const int v = v0 + lane;
-      const int sc = v <= n ? lds16(s.msu + 2u * v) : 0;
-      const unsigned bal = __ballot_sync(kFull, sc != 0);
+      const unsigned sc = v <= n ? (unsigned)lds16(s.msu + 2u * v) : 0u;
+      const unsigned bal = __ballot_sync(kFull, sc != 0u);
       if (sc) {
-        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-        src[pos] = off + v;
-        dst[pos] = off + sc;
+        const int pos = __popc(bal & below);
+        src[pos] = make_uint2(off + (unsigned)v, 0u);
+        dst[pos] = make_uint2(off + sc, 0u);
       }
-      cnt += __popc(bal);
+      const int adv = __popc(bal);
+      src += adv;
+      dst += adv;
     }
   }
   __syncwarp();
@@ -510,7 +526,7 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   if (ms < 0) status = -5;
   int np = 0;
   auto enumerate = [&]() {
-    link_pass(L, s, lane, false);
+    link_pass<false>(L, s, lane);
     const int len = trace_path(L, s, ms, lane, rp);
     int c = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
       if (idx < pmax) { sts16(plist + 4u * idx, u); sts16(plist + 4u * idx + 2u, v); }
