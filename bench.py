@@ -12,9 +12,10 @@ A "step" is ONE `l2s_step` launch over one batch: swap + re-evaluation (est, lst
 machine edges + reward/incumbent/tabu + critical path + N5 move set for every instance of the batch.
 
   value : device-resident throughput (state and action tape already in HBM), CUDA events, max over ranks.
-  e2e   : the same steps through the drop-in `JsspN5.step(actions, device)` Python API with HOST data:
-          Python action lists in, pinned H2D copy, kernel, D2H of the move sets, Python move lists out.
-  e2e_capi : the same through the C-ABI `l2s_step_host` with host numpy buffers (no Python list building).
+  e2e   : the same steps through the C-ABI `l2s_step_host` with HOST buffers: host actions in, pinned H2D copy,
+          kernel, D2H of move sets / rewards / makespans, host arrays out, stream synchronised every step.
+  e2e_python_api : the same through the drop-in `JsspN5.step(actions, device)` (Python lists in and out).
+  evaluator : `Evaluator.forward` on the int64 COO edge lists of the same schedules (graphs/s, GB/s).
   roofline : algorithmic bytes of one step (SURVEY.md 8d formula) / mean launch duration vs measured HBM peak.
   cpu_baseline : the CPU oracle port of the reference path (oracle/l2s_oracle.py) on a bounded sample.
 
@@ -72,26 +73,25 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
-
-    def _loop(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.05)
+        self.index, self.rows, self.proc = index, [], None
 
     def start(self):
-        self.thread = threading.Thread(target=self._loop, daemon=True)
-        self.thread.start()
+        # one long-lived nvidia-smi in loop mode (20 ms period); its stdout is parsed at stop()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=10)
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=10)
+                self.rows = [[c.strip() for c in ln.split(",")] for ln in out.strip().split("\n") if ln.strip()]
+            except Exception:
+                self.rows = []
         sm, mx, reasons = [], 0.0, set()
         for r in self.rows:
             try:
@@ -315,13 +315,36 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     t_capi = time.perf_counter() - t0
     assert not host_out["status"].any()
+
+    # ---- phase 4: stateless evaluator (Evaluator.forward drop-in) on the current schedules ----------------
+    from l2s_b200 import Evaluator
+    ev = Evaluator()
+    ev_in = []
+    for r in range(REPLICAS):
+        state, fa, done = envs[r].observe()
+        ei = torch.cat([state[1], state[2]], dim=1).contiguous()
+        dur = torch.zeros((B, n1), dtype=torch.int64, device=dev)
+        dur[:, 1:-1] = torch.from_numpy(envs[r].instances[:, 0].reshape(B, -1).astype(np.int64)).to(dev)
+        ev_in.append((ei, dur.reshape(-1, 1)))
+    k_ev = max(4, min(K, 40))
+    for r in range(min(REPLICAS, 3)):
+        ev.forward(ev_in[r][0], ev_in[r][1], n_j, n_m)
+    barrier()
+    e0.record(stream)
+    for k in range(k_ev):
+        ei, dur = ev_in[k % REPLICAS]
+        est, lst, mk = ev.forward(ei, dur, n_j, n_m)
+    e1.record(stream)
+    barrier()
+    ms_ev = e0.elapsed_time(e1)
+    assert torch.equal(mk.reshape(-1), envs[(k_ev - 1) % REPLICAS].current_objs.reshape(-1))
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
-    times = torch.tensor([ms_dev / 1e3, t_py, t_capi], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_dev / 1e3, t_py, t_capi, ms_ev / 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_py, t_capi = [float(v) for v in times.cpu()]
+    t_dev, t_py, t_capi, t_ev = [float(v) for v in times.cpu()]
     value = world * B * K / t_dev
     e2e_py = world * B * k_e2e / t_py
     e2e_capi = world * B * K / t_capi
@@ -340,7 +363,7 @@ def run_ours(args, rank, world, local_rank):
                 traffic = None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cb, cs = (24, 10) if n <= 400 else (2, 3)
+            cb, cs = (64, 150) if n <= 400 else (4, 10)
             t0 = time.perf_counter()
             rate = cpu_port_rate(n_j, n_m, cb, cs, 2, 1)
             cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
@@ -356,12 +379,19 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "%d independent batches stepped round-robin: per-step working set x%d > 126 MB L2"
                              % (REPLICAS, REPLICAS),
                        "mean_pairs": pbar, "parallelism": "instance-sharded x%d" % world},
-            "e2e": {"value": e2e_py, "unit": UNIT, "api": "JsspN5.step(actions: list, device) -> lists",
+            "e2e": {"value": e2e_capi, "unit": UNIT,
+                    "api": "C-ABI l2s_step_host: host int32 actions in, host pairs/npairs/done/reward/makespan/status out",
                     "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": int(envs[0]._lib.l2s_pmax(envs[0]._h)) * B * 8 + B * 21,
-                    "steps": k_e2e},
-            "e2e_capi": {"value": e2e_capi, "unit": UNIT, "api": "l2s_step_host (host numpy buffers)",
-                         "h2d_bytes_per_step": B * 8,
-                         "d2h_bytes_per_step": int(envs[0]._lib.l2s_pmax(envs[0]._h)) * B * 8 + B * 21},
+                    "steps": K},
+            "e2e_python_api": {"value": e2e_py, "unit": UNIT,
+                               "api": "drop-in JsspN5.step(actions: list[B][2], device) -> (state, reward, list[B][P][2], done); "
+                                      "dominated by building ~%d Python lists per step, as the reference API requires" % int(B * (1 + pbar)),
+                               "steps": k_e2e},
+            "evaluator": {"graphs_per_s": world * B * k_ev / t_ev, "ms_per_call": 1e3 * t_ev / k_ev,
+                          "api": "Evaluator.forward(edge_index int64 COO, duration int64, n_j, n_m)",
+                          "algorithmic_bytes_per_graph": 8 * n1 + 16 * (n_j * (n_m + 1) + e_mc) + 8 * n1 + 4,
+                          "achieved_gbs": (8 * n1 + 16 * (n_j * (n_m + 1) + e_mc) + 8 * n1 + 4) * B * k_ev / t_ev / 1e9 / 1.0,
+                          "frac_of_peak": (8 * n1 + 16 * (n_j * (n_m + 1) + e_mc) + 8 * n1 + 4) * B * k_ev / t_ev / 1e9 / peak},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "l2s::step_kernel",
@@ -376,8 +406,8 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="20x15")
     ap.add_argument("--batch", type=int, default=8192)

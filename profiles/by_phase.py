@@ -1,13 +1,37 @@
-"""Share of executed warp instructions / stall samples per phase of l2s::step_kernel
-(input: `ncu --page source --csv --print-source cuda,sass` export).  usage: by_phase.py file.csv insts_per_launch B"""
+"""Share of executed warp instructions / stall samples per phase of l2s::step_kernel.
+Input: `ncu -i X.ncu-rep --page source --csv --print-source cuda,sass` export.  Phase boundaries are found by
+searching the CURRENT sources for their marker lines, so run it against the sources the profile was built from.
+usage: by_phase.py file.csv [warp_instructions_per_launch instances_per_launch]"""
 import csv
+import os
+import re
 import sys
 
-PH = {"l2s_device.cuh": [(75, 125, "smem helpers (ld/st)"), (126, 132, "fill_pending"), (133, 150, "stage"), (151, 193, "wavefront"),
-                          (194, 218, "evaluate glue"), (219, 241, "link_pass"), (242, 262, "apply_swap"), (263, 286, "trace_path"),
-                          (287, 322, "n5_moves")],
-      "l2s_kernels.cuh": [(262, 270, "div_rn (x)"), (303, 331, "prologue+search"), (332, 352, "swap glue"), (353, 380, "eval glue/S,T rows"),
-                          (381, 400, "x output"), (401, 420, "emc output"), (421, 438, "path+moves glue"), (439, 475, "scalars")]}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MARKS = {
+    "l2s_device.cuh": [("smem helpers", r"smem_addr\(const void"), ("fill_pending", r"void fill_pending"),
+                       ("stage", r"void stage_instance"), ("wavefront", r"bool wavefront\("),
+                       ("evaluate glue", r"int evaluate_instance"), ("link_pass", r"void link_pass"),
+                       ("apply_swap", r"int apply_swap"), ("trace_path", r"int trace_path"),
+                       ("n5_moves", r"int n5_moves"), ("rng", r"uint64_t mix64")],
+    "l2s_kernels.cuh": [("setup kernels", r"__global__ void load_kernel"), ("div_rn", r"float div_rn"),
+                        ("prologue+search", r"step_kernel\(const __grid_constant__"), ("swap glue", r"// 1\. N5 swap"),
+                        ("eval glue / S,T rows", r"// 2\. evaluate"), ("x output", r"// 3\. node features"),
+                        ("emc output", r"// 4\. machine edges"), ("path+moves glue", r"// 5\. critical path"),
+                        ("scalars", r"// 6\. reward"), ("other kernels", r"// K fused steps")],
+}
+ranges = {}
+for f, marks in MARKS.items():
+    lines = open(os.path.join(ROOT, "l2s_b200", "csrc", f)).read().split("\n")
+    starts = []
+    for name, pat in marks:
+        for i, ln in enumerate(lines):
+            if re.search(pat, ln):
+                starts.append((i + 1, name))
+                break
+    starts.sort()
+    ranges[f] = [(s, (starts[k + 1][0] - 1 if k + 1 < len(starts) else 10 ** 9), nm) for k, (s, nm) in enumerate(starts)]
+
 rows = list(csv.reader(open(sys.argv[1])))
 cur, hdr, agg = None, None, {}
 for r in rows:
@@ -20,7 +44,7 @@ for r in rows:
     if hdr and len(r) > 10 and r[0].isdigit():
         ln = int(r[0])
         name = cur + ":other"
-        for lo, hi, nm in PH.get(cur, []):
+        for lo, hi, nm in ranges.get(cur, []):
             if lo <= ln <= hi:
                 name = nm
         try:
