@@ -461,41 +461,42 @@ int l2s_poll_error(l2s_handle h, int* instance_out, void* stream) {
 int64_t l2s_eval_coo_workspace_bytes(int n_j, int n_m, int64_t batch) {
   if (n_j < 1 || n_m < 1 || batch < 1) return L2S_ERR_INVALID_ARG;
   const long long node_stride = ru((long long)n_j * n_m + 2, 8);
-  return 2 * batch * node_stride * 2 + 16;
+  return batch * node_stride * 2 + 16;
 }
 
 int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duration, int duration_is_i64, int n_j,
                  int n_m, int64_t batch, float* est, float* lst, float* makespan, void* workspace,
                  int64_t workspace_bytes, int32_t* status_flag, int device, void* stream) {
   if (!edge_index || !duration || !est || !lst || !makespan || !workspace || !status_flag || batch < 1 ||
-      n_j < 1 || n_m < 1 || n_edges < 0)
+      n_j < 2 || n_m < 1 || n_edges < 0)
     return L2S_ERR_INVALID_ARG;
   const long long n = (long long)n_j * n_m;
-  if (n + 2 > 65535) return L2S_ERR_UNSUPPORTED_SHAPE;
+  if (n + 2 > 65535 || n_m > 32) return L2S_ERR_UNSUPPORTED_SHAPE;
+  if (batch * (n + 2) >= (1ll << 31)) return L2S_ERR_INVALID_ARG;   // 32-bit node ids per call
   if (workspace_bytes < l2s_eval_coo_workspace_bytes(n_j, n_m, batch)) return L2S_ERR_INVALID_ARG;
+  // a batch of complete selections has exactly this many edges (duplicates are caught on the device)
+  if (n_edges != batch * ((long long)n_j * (n_m + 1) + (long long)n_m * (n_j - 1))) return L2S_ERR_BAD_GRAPH;
   CU(cudaSetDevice(device));
   cudaStream_t s = (cudaStream_t)stream;
   CooEvalArgs a;
   memset(&a, 0, sizeof(a));
-  a.n_j = n_j; a.n_m = n_m; a.n = (int)n; a.n1 = (int)n + 2; a.n1p = ru(a.n1, 4); a.node_stride = ru(a.n1, 8);
+  a.L = make_layout(n_j, n_m);
+  const Layout& L = a.L;
   a.B = batch;
   a.duration = duration;
   a.dur_i64 = duration_is_i64;
-  const size_t links = (size_t)batch * a.node_stride * 2;
+  const size_t links = (size_t)batch * L.node_stride * 2;
   a.ws.msucc = (uint16_t*)workspace;
-  a.ws.mpred = (uint16_t*)((char*)workspace + links);
-  a.ws.conj_count = (unsigned long long*)((char*)workspace + 2 * links);
+  a.ws.conj_count = (unsigned long long*)((char*)workspace + links);
   a.ws.flag = status_flag;
   a.est = est; a.lst = lst; a.ms = makespan;
   a.expect_conj = batch * ((long long)n_j * (n_m + 1));
-  int off = 0;
-  a.off_tq = off;    off += 2 * a.n1p * 4;
-  a.off_durw = off;  off += a.node_stride * 2;
-  a.off_succ = off;  off += a.node_stride * 2;
-  a.off_pred = off;  off += a.node_stride * 2;
-  a.off_heads = off; off += 128;
+  // shared memory: tq | walk | durw (offsets of the env layout), then successors and the head list
+  int off = L.off_aux;
+  a.off_succ = off;  off += L.node_stride * 2;
+  a.off_heads = off; off += 64;
   a.bytes = ru(off, 16);
-  const int W = pick_warps(a.bytes);
+  const int W = pick_warps(a.bytes, 4);
   if (!W) return L2S_ERR_UNSUPPORTED_SHAPE;
   static bool attr_set[64] = {false};
   if (device >= 0 && device < 64 && !attr_set[device]) {
@@ -503,14 +504,19 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
     CU(cudaFuncSetAttribute(coo_eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[device] = true;
   }
-  CU(cudaMemsetAsync(workspace, 0, 2 * links + 16, s));
+  CU(cudaMemsetAsync(workspace, 0, links + 16, s));
   CU(cudaMemsetAsync(status_flag, 0, 4, s));
-  if (n_edges > 0) {
-    const long long blocks = (n_edges + 255) / 256;
-    coo_ingest_kernel<<<(unsigned)blocks, 256, 0, s>>>((const long long*)edge_index, n_edges, n_j, n_m, batch,
-                                                       a.node_stride, a.ws);
-    CU(cudaGetLastError());
-  }
+  CooIngestArgs g;
+  memset(&g, 0, sizeof(g));
+  g.ei = (const long long*)edge_index;
+  g.E = n_edges; g.B = batch; g.n_j = n_j; g.n_m = n_m; g.n = (int)n; g.n1 = (int)n + 2; g.node_stride = L.node_stride;
+  g.magic_n1 = (unsigned)((1ull << 32) / (unsigned)(n + 2)) + 1u;
+  g.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
+  g.ws = a.ws;
+  long long blocks = (n_edges + 4 * 1024 - 1) / (4 * 1024);   // ~4 edges per thread
+  if (blocks < 1) blocks = 1;
+  coo_ingest_kernel<<<(unsigned)blocks, 1024, 0, s>>>(g);
+  CU(cudaGetLastError());
   coo_eval_kernel<<<(unsigned)((batch + W - 1) / W), W * 32, (size_t)W * a.bytes, s>>>(a);
   CU(cudaGetLastError());
   return L2S_OK;

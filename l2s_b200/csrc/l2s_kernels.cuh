@@ -617,79 +617,78 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
 
 // ------------------------------------------------------------------------------------------------------
 // Stateless evaluator for COO input: drop-in for Evaluator.forward (env/message_passing_evl.py:161-199).
-//   pass 1 (coo_ingest_kernel): one thread per edge, coalesced int64 reads; conjunctive arcs are implicit in
-//           the node numbering and only counted, machine arcs are scattered into uint16 succ/pred arrays.
-//   pass 2 (coo_eval_kernel): one warp per graph, same wavefront as the environment but following the
-//           succ/pred chains (the machine of an operation is not part of this API).
+//   pass 1 (coo_ingest_kernel): edges are read once, coalesced (int64 pairs); conjunctive arcs are implicit in
+//           the node numbering and only counted, machine arcs are scattered into a uint16 successor array.
+//   pass 2 (coo_eval_kernel): one warp per graph: stage successors + durations, follow the n_m machine chains
+//           from their heads into walk rows (the machine of an operation is not part of this API), then run
+//           the SAME wavefront as the environment and write est / lst / makespan as float32.
 // ------------------------------------------------------------------------------------------------------
 struct CooWs {
   uint16_t* msucc;      // [B][node_stride]
-  uint16_t* mpred;      // [B][node_stride]
   unsigned long long* conj_count;
   int32_t* flag;        // device status word
 };
 
-__global__ void coo_ingest_kernel(const long long* __restrict__ ei, long long E, int n_j, int n_m, long long B,
-                                  int node_stride, CooWs ws) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = n_j * n_m, n1 = n + 2;
-  int conj = 0;
-  if (e < E) {
-    const long long u = ei[e], v = ei[E + e];
-    const long long bu = u / n1, bv = v / n1;
-    const int ul = (int)(u - bu * n1), vl = (int)(v - bv * n1);
-    if (u < 0 || v < 0 || bu != bv || bu >= B) {
-      atomicCAS(ws.flag, 0, -5);
-    } else if (ul == 0) {
-      if (vl >= 1 && vl <= n && (vl - 1) % n_m == 0) conj = 1; else atomicCAS(ws.flag, 0, -5);
-    } else if (vl == n + 1) {
-      if (ul >= 1 && ul <= n && ul % n_m == 0) conj = 1; else atomicCAS(ws.flag, 0, -5);
-    } else if (ul > n || vl == 0) {
-      atomicCAS(ws.flag, 0, -5);   // edge out of T or into S
-    } else if (vl == ul + 1 && ul % n_m != 0) {
-      conj = 1;
-    } else {
-      ws.msucc[bu * node_stride + ul] = (uint16_t)vl;
-      ws.mpred[bu * node_stride + vl] = (uint16_t)ul;
-    }
-  }
-  const unsigned bal = __ballot_sync(kFull, conj);
-  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(ws.conj_count, (unsigned long long)__popc(bal));
+struct CooIngestArgs {
+  const long long* ei;
+  long long E, B;
+  int n_j, n_m, n, n1, node_stride;
+  unsigned magic_n1, magic_nm;   // ceil(2^32 / d): exact x / d for x < 2^31 / d ... see fast_div
+  CooWs ws;
+};
+
+// x / d for 0 <= x < 2^31 via one 32x32->64 multiply (magic = floor(2^32/d)+1, exact while x*d' error < 1;
+// the host only enables the 32-bit path when N = B*n1 < 2^31 and falls back to 64-bit division otherwise).
+__device__ __forceinline__ unsigned fast_div(unsigned x, unsigned magic, unsigned d) {
+  unsigned qd = __umulhi(x, magic);
+  // magic is floor(2^32/d)+1: q can overshoot by one for large x; correct it
+  return qd - ((qd * d > x) ? 1u : 0u);
 }
 
-// chain-following wavefront: lane walks a machine chain through nxt[] (msucc forward / mpred backward)
-__device__ __forceinline__ bool wavefront_chain(int n, int n1p, volatile int32_t* tq, const uint16_t* durw,
-                                                const uint16_t* nxt, int head, int dir, int& last) {
-  const int base = dir ? n1p : 0;
-  const int nbr = dir ? 1 : -1;
-  const int bflag = dir ? kLastFlag : kFirstFlag;
-  int prevval = 0, cur = head, dw = 0;
-  bool more = cur != 0;
-  if (more) dw = durw[cur];
-  int budget = n + 2;
-  while (true) {
-    if (more) {
-      int nb = tq[base + cur + nbr];
-      nb = (dw & bflag) ? 0 : nb;
-      if (nb >= 0) {
-        const int val = max(prevval, nb) + (dw & kDurMask);
-        tq[base + cur] = val;
-        prevval = val;
-        cur = nxt[cur];
-        more = cur != 0;
-        if (more) dw = durw[cur];
+__global__ void __launch_bounds__(1024) coo_ingest_kernel(const __grid_constant__ CooIngestArgs a) {
+  const int n = a.n, n1 = a.n1, n_m = a.n_m;
+  int conj = 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < a.E; e += (long long)gridDim.x * blockDim.x) {
+    const long long u = a.ei[e], v = a.ei[a.E + e];
+    bool bad = u < 0 || v < 0 || u >= a.B * n1 || v >= a.B * n1;
+    if (!bad) {
+      const unsigned bu = fast_div((unsigned)u, a.magic_n1, (unsigned)n1), bv = fast_div((unsigned)v, a.magic_n1, (unsigned)n1);
+      const int ul = (int)((unsigned)u - bu * (unsigned)n1), vl = (int)((unsigned)v - bv * (unsigned)n1);
+      bad = bu != bv;
+      if (!bad) {
+        // position of u inside its job: (ul-1) % n_m ; last of job <=> ul % n_m == 0
+        const unsigned ju = fast_div((unsigned)(ul > 0 ? ul - 1 : 0), a.magic_nm, (unsigned)n_m);
+        const int pos_u = ul - 1 - (int)(ju * (unsigned)n_m);
+        if (ul == 0) {                       // S -> first operation of a job
+          const unsigned jv = fast_div((unsigned)(vl > 0 ? vl - 1 : 0), a.magic_nm, (unsigned)n_m);
+          if (vl >= 1 && vl <= n && vl - 1 - (int)(jv * (unsigned)n_m) == 0) ++conj; else bad = true;
+        } else if (vl == n + 1) {            // last operation of a job -> T
+          if (ul <= n && pos_u == n_m - 1) ++conj; else bad = true;
+        } else if (ul > n || vl == 0) {
+          bad = true;                        // edge out of T or into S
+        } else if (vl == ul + 1 && pos_u != n_m - 1) {
+          ++conj;                            // job arc
+        } else {
+          a.ws.msucc[(size_t)bu * a.node_stride + ul] = (uint16_t)vl;   // machine arc
+        }
       }
     }
-    __syncwarp();
-    if (!__any_sync(kFull, more)) break;
-    if (--budget < 0) { last = prevval; return false; }
+    if (bad) atomicCAS(a.ws.flag, 0, -5);
   }
-  last = prevval;
-  return true;
+  // one atomic per CTA
+  __shared__ int warp_sums[32];
+  for (int o = 16; o; o >>= 1) conj += __shfl_xor_sync(kFull, conj, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = conj;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int t = threadIdx.x < (blockDim.x >> 5) ? warp_sums[threadIdx.x] : 0;
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+    if (threadIdx.x == 0 && t) atomicAdd(a.ws.conj_count, (unsigned long long)t);
+  }
 }
 
 struct CooEvalArgs {
-  int n_j, n_m, n, n1, n1p, node_stride;
+  Layout L;            // tq + walk + durw offsets are reused; aux is not needed
   long long B;
   const void* duration;
   int dur_i64;
@@ -697,102 +696,108 @@ struct CooEvalArgs {
   float* est;
   float* lst;
   float* ms;
-  int bytes;   // smem per graph
-  int off_tq, off_durw, off_succ, off_pred, off_heads;
+  int bytes;           // smem per graph
+  int off_succ, off_heads;
   long long expect_conj;
 };
 
-__global__ void coo_eval_kernel(const __grid_constant__ CooEvalArgs a) {
+__global__ void __launch_bounds__(128, 10) coo_eval_kernel(const __grid_constant__ CooEvalArgs a) {
   extern __shared__ __align__(16) unsigned char smem_coo[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + w;
   if (b >= a.B) return;
-  unsigned char* base = smem_coo + (size_t)w * a.bytes;
-  int32_t* tq = reinterpret_cast<int32_t*>(base + a.off_tq);
-  uint16_t* durw = reinterpret_cast<uint16_t*>(base + a.off_durw);
-  uint16_t* succ = reinterpret_cast<uint16_t*>(base + a.off_succ);
-  uint16_t* pred = reinterpret_cast<uint16_t*>(base + a.off_pred);
-  uint16_t* heads = reinterpret_cast<uint16_t*>(base + a.off_heads);   // [32] heads, [32] tails
-  const int n = a.n, n1 = a.n1, n_m = a.n_m;
+  const Layout& L = a.L;
+  const uint32_t base = smem_addr(smem_coo) + (uint32_t)w * (uint32_t)a.bytes;
+  const Inst s = inst_view(L, base);
+  const uint32_t succ = base + a.off_succ, heads = base + a.off_heads;   // uint16 [node_stride], uint16 [32]
+  const int n = L.n, n1 = L.n1, n_m = L.n_m, n_j = L.n_j;
   if (b == 0 && lane == 0 && *a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
 
-  // stage: machine links (uint16, 16-byte vectors) and durations -> node words
-  const uint4* gs = reinterpret_cast<const uint4*>(a.ws.msucc + b * a.node_stride);
-  const uint4* gp = reinterpret_cast<const uint4*>(a.ws.mpred + b * a.node_stride);
-  for (int i = lane; i < a.node_stride / 8; i += 32) {
-    reinterpret_cast<uint4*>(succ)[i] = gs[i];
-    reinterpret_cast<uint4*>(pred)[i] = gp[i];
-  }
+  // stage: machine successors (uint16, 16-byte vectors) and durations -> node words
+  const uint4* gs = reinterpret_cast<const uint4*>(a.ws.msucc + b * L.node_stride);
+  for (int i = lane; i < L.node_stride / 8; i += 32) sts128(succ + 16 * i, gs[i]);
   int bad = 0;
-  for (int i = lane; i < n1; i += 32) {
-    long long d = a.dur_i64 ? reinterpret_cast<const long long*>(a.duration)[b * n1 + i]
-                            : (long long)reinterpret_cast<const int32_t*>(a.duration)[b * n1 + i];
-    if (d < 0 || d > kDurMask) { bad = 1; d = 0; }
-    int word = (int)d;
-    if (i >= 1 && i <= n) {
-      const int pos = (i - 1) % n_m;
-      word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
-    } else if (d != 0) {
-      bad = 1;
+  {
+    int pos = lane == 0 ? n_m - 1 : (lane - 1) % n_m;   // (i-1) mod n_m, advanced by 32 per trip
+    const int step = 32 % n_m;
+    for (int i = lane; i < n1; i += 32) {
+      long long d = a.dur_i64 ? reinterpret_cast<const long long*>(a.duration)[b * n1 + i]
+                              : (long long)reinterpret_cast<const int32_t*>(a.duration)[b * n1 + i];
+      if (d < 0 || d > kDurMax) { bad = 1; d = 0; }
+      int word = (int)d;
+      if (i >= 1 && i <= n) word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
+      else if (d != 0) bad = 1;
+      sts16(s.durw + 2u * i, word);
+      pos += step;
+      if (pos >= n_m) pos -= n_m;
     }
-    durw[i] = (uint16_t)word;
   }
-  const int4 pending = make_int4(-1, -1, -1, -1);
-  for (int i = lane; i < 2 * a.n1p / 4; i += 32) reinterpret_cast<int4*>(tq)[i] = pending;
+  fill_pending(L, s, lane, true);
   __syncwarp();
-  // heads (no machine predecessor) and tails (no machine successor), ascending
-  int nh = 0, nt = 0, narc = 0;
+  // heads = operations nobody points to.  Mark successors in tq's (still unused) backward half as a bitmap.
+  const uint32_t bits = s.tq + 4u * L.n1p;          // reuse: n1 bits <= 4*n1p bytes
+  for (int i = lane; i < (n1 + 31) / 32; i += 32) sts32(bits + 4u * i, 0);
+  __syncwarp();
+  int narc = 0;
+  for (int v = 1 + lane; v <= n; v += 32) {
+    const int sc = lds16(succ + 2u * v);
+    if (sc) { atomicOr(reinterpret_cast<unsigned*>(smem_coo + (bits - smem_addr(smem_coo))) + (sc >> 5), 1u << (sc & 31)); ++narc; }
+  }
+  narc = __reduce_add_sync(kFull, narc);
+  __syncwarp();
+  int nh = 0;
   for (int v0 = 1; v0 <= n; v0 += 32) {
     const int v = v0 + lane;
-    const bool ish = v <= n && pred[v] == 0, ist = v <= n && succ[v] == 0;
-    const unsigned bh = __ballot_sync(kFull, ish), bt = __ballot_sync(kFull, ist);
-    const int ph = nh + __popc(bh & ((1u << lane) - 1u)), pt = nt + __popc(bt & ((1u << lane) - 1u));
-    if (ish && ph < 32) heads[ph] = (uint16_t)v;
-    if (ist && pt < 32) heads[32 + pt] = (uint16_t)v;
+    const bool ish = v <= n && !((lds32(bits + 4u * (v >> 5)) >> (v & 31)) & 1);
+    const unsigned bh = __ballot_sync(kFull, ish);
+    const int ph = nh + __popc(bh & ((1u << lane) - 1u));
+    if (ish && ph < 32) sts16(heads + 2u * ph, v);
     nh += __popc(bh);
-    nt += __popc(bt);
-    narc += __popc(__ballot_sync(kFull, v <= n && succ[v] != 0));
   }
   __syncwarp();
   bad = __reduce_or_sync(kFull, bad);
-  // a complete selection has n_m chains covering all operations: n - n_m machine arcs
-  if (bad || nh != nt || nh > 32 || narc != n - nh) {
+  // a complete selection has exactly n_m machine chains of n_j operations: n_m heads, n - n_m machine arcs
+  if (bad || nh != n_m || narc != n - n_m) {
     if (lane == 0) atomicCAS(a.ws.flag, 0, bad ? -6 : -5);
     return;
   }
-  bool ok;
-  int last = 0, fwd_last = 0;
-  if (nh <= 16) {
-    const int c = lane & 15, dir = lane >> 4;
-    const int head = c < nh ? heads[dir * 32 + c] : 0;
-    ok = wavefront_chain(n, a.n1p, tq, durw, dir ? pred : succ, head, dir, last);
-    fwd_last = dir ? 0 : last;
-  } else {
-    ok = wavefront_chain(n, a.n1p, tq, durw, succ, lane < nh ? heads[lane] : 0, 0, last);
-    fwd_last = last;
-    if (ok) {
-      int l2;
-      ok = wavefront_chain(n, a.n1p, tq, durw, pred, lane < nh ? heads[32 + lane] : 0, 1, l2);
+  // follow chain `lane` from its head into walk row `lane` (pointer chase, n_j steps)
+  int chain_ok = 1;
+  if (lane < n_m) {
+    int v = lds16(heads + 2u * lane);
+    for (int k = 0; k < n_j; ++k) {
+      if (v == 0) { chain_ok = 0; break; }
+      const int nx = lds16(succ + 2u * v);
+      sts32(s.walk + 4u * (lane * n_j + k), (int)make_walk(v, lds16(s.durw + 2u * v), false, k == n_j - 1));
+      v = nx;
     }
+    if (v != 0) chain_ok = 0;      // longer than n_j (or a cycle)
   }
-  // every operation must have been reached (a pure machine cycle has no head)
-  int pend = 0;
-  for (int v = 1 + lane; v <= n; v += 32) pend |= (tq[v] < 0) | (tq[a.n1p + v] < 0);
-  pend = __reduce_or_sync(kFull, pend);
-  if (!ok || pend) {
+  chain_ok = __reduce_and_sync(kFull, chain_ok);
+  fill_pending(L, s, lane, true);  // the bitmap lived in the backward half
+  __syncwarp();
+  const int ms = chain_ok ? evaluate_instance(L, s, lane, true) : -1;
+  if (ms < 0) {
     if (lane == 0) atomicCAS(a.ws.flag, 0, -5);
     return;
   }
-  const int ms = __reduce_max_sync(kFull, fwd_last);
+  const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   int qs = 0;
-  for (int j = lane; j < a.n_j; j += 32) qs = max(qs, tq[a.n1p + j * n_m + 1]);
+  for (int j = lane; j < n_j; j += 32) qs = max(qs, lds32(q + 4u * (j * n_m + 1)));
   qs = __reduce_max_sync(kFull, qs);
+  if (lane == 0) {
+    sts32(fin, 0);
+    sts32(q, qs);
+    sts32(fin + 4u * (n + 1), ms);
+    sts32(q + 4u * (n + 1), 0);
+  }
+  __syncwarp();
   float* eo = a.est + b * n1;
   float* lo = a.lst + b * n1;
   for (int i = lane; i < n1; i += 32) {
-    const int d = durw[i] & kDurMask;
-    eo[i] = (float)(i == 0 ? 0 : (i == n1 - 1 ? ms : tq[i] - d));
-    lo[i] = (float)(i == 0 ? ms - qs : (i == n1 - 1 ? ms : ms - tq[a.n1p + i]));
+    const int d = lds16(s.durw + 2u * i) & kDurMask;
+    eo[i] = (float)(lds32(fin + 4u * i) - d);
+    lo[i] = (float)(ms - lds32(q + 4u * i));
   }
   if (lane == 0) a.ms[b] = (float)ms;
 }

@@ -69,7 +69,7 @@ class JsspN5:
     """N5 local-search environment for batches of JSSP instances (reference: env/environment.py:39-423)."""
 
     def __init__(self, n_job, n_mch, low, high, reward_type='yaoxin', fea_norm_const=1000,
-                 evaluator_type='message-passing', pmax=32):
+                 evaluator_type='message-passing', pmax=None):
         self.n_job = n_job
         self.n_mch = n_mch
         self.n_oprs = n_job * n_mch
@@ -85,7 +85,8 @@ class JsspN5:
         # 'message-passing' and 'CPM' give identical numbers in the reference (env/message_passing_evl.py
         # :367-371); both are served by the same kernel here.
         self.evaluator_type = evaluator_type
-        self.pmax = pmax
+        # capacity of the per-instance move list; grown automatically if a reset finds more N5 pairs
+        self.pmax = pmax if pmax else (32 if n_job <= 30 else (64 if n_job <= 60 else 128))
         self.instance_offset = 0      # global index of the first instance (multi-GPU sharding)
         self._h = None
         self._key = None
@@ -169,7 +170,17 @@ class JsspN5:
             assert False, 'Initial solution type = "plist", "spt", "fdd-divide-mwkr".'
         self._poll("reset")
         self.itr = 0
-        state, _, fa, done = self._launch(None, device, is_reset=True)
+        try:
+            state, _, fa, done = self._launch(None, device, is_reset=True)
+        except L2SError as e:
+            if e.status != _capi.STATUS["PAIR_OVERFLOW"] or self.pmax >= 4096:
+                raise
+            # more N5 pairs than the move list holds: start over with a larger list (nothing to migrate at reset)
+            sol = self.solutions().cpu().numpy()
+            self.pmax *= 2
+            self.close()
+            self._key = None
+            return self.reset(instances, init_type, device, plot=plot, init_solutions=sol)
         return state, fa, done
 
     def step(self, actions, device, plot=False):

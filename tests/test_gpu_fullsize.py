@@ -117,3 +117,36 @@ def test_input_validation_errors():
         JsspN5(6, 6, 1, 99).reset(inst, "fdd-divide-mwkr", "cuda", init_solutions=sol)
     with pytest.raises(L2SError):
         JsspN5(40, 40, 1, 99).reset(gen_instances(40, 40, 1, 1), "spt", "cuda")      # n_m > 32 unsupported
+
+
+@pytest.mark.parametrize("n_j,n_m,B", [(20, 15, 4096), (10, 10, 300), (16, 16, 64), (100, 20, 32), (150, 25, 16), (7, 32, 40)])
+def test_evaluator_coo_full_size(n_j, n_m, B):
+    """Evaluator.forward on shuffled int64 COO == the integer est/lst of the environment (itself checked against
+    the oracle above) for the same schedules; malformed inputs are rejected."""
+    from l2s_b200 import Evaluator, JsspN5, L2SError
+    inst = gen_instances(n_j, n_m, B, seed=3 * n_j + n_m)
+    env = JsspN5(n_j, n_m, 1, 99)
+    state, fa, done = env.reset(inst, "spt", "cuda")
+    env.run("random", 15, seed=1)
+    state, fa, done = env.observe()
+    ex = env.export_state()
+    n1 = n_j * n_m + 2
+    ei = torch.cat([state[1], state[2]], dim=1)
+    ei = ei[:, torch.randperm(ei.shape[1], device=ei.device)]
+    dur = torch.zeros((B, n1), dtype=torch.int64, device="cuda")
+    dur[:, 1:-1] = torch.from_numpy(inst[:, 0].reshape(B, -1).astype(np.int64)).cuda()
+    est, lst, ms = Evaluator().forward(ei, dur.reshape(-1, 1), n_j, n_m)
+    assert torch.equal(est.reshape(B, n1), ex["est"].float()) and torch.equal(lst.reshape(B, n1), ex["lst"].float())
+    assert torch.equal(ms, env.current_objs)
+    # a duplicated machine arc / a missing edge / a reversed arc are rejected (conjunctive arcs are implicit in
+    # the node numbering: they are counted, not verified one by one)
+    bad = torch.cat([state[1], state[2]], dim=1)
+    bad[:, -1] = bad[:, -2]
+    with pytest.raises(L2SError):
+        Evaluator().forward(bad, dur.reshape(-1, 1), n_j, n_m)
+    with pytest.raises(L2SError):
+        Evaluator().forward(ei[:, :-1], dur.reshape(-1, 1), n_j, n_m)
+    mc = state[2].clone()
+    mc[:, 0] = torch.flip(mc[:, 0], dims=[0])           # reverse one machine arc -> 2-cycle or broken chain
+    with pytest.raises(L2SError):
+        Evaluator().forward(torch.cat([state[1], mc], dim=1), dur.reshape(-1, 1), n_j, n_m)
