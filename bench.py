@@ -291,9 +291,8 @@ def run_ours(args, rank, world, local_rank):
         r = k % REPLICAS
         hb.append((r, np.ascontiguousarray(host_tapes[r][p3[r]])))
         p3[r] += 1
-    host_out = dict(pairs=np.empty((B, envs[0].pmax, 2), np.int32), npairs=np.empty(B, np.int32),
-                    done=np.empty(B, np.uint8), rew=np.empty(B, np.float32), ms=np.empty(B, np.float32),
-                    status=np.empty(B, np.int32))
+    # host results are read in place from the handle's pinned buffers (l2s_host_buffers): zero extra copies
+    sink = 0
 
     def capi_step(r, acts):
         o = outs[r]
@@ -301,10 +300,9 @@ def run_ours(args, rank, world, local_rank):
                           x=o["x"].data_ptr(), edge_index_mc=o["emc"].data_ptr(), makespan=o["ms"].data_ptr(),
                           incumbent=o["inc"].data_ptr(), reward=o["rew"].data_ptr(), done=o["done"].data_ptr(),
                           pairs=None, npairs=None, status=None)
-        _capi.check(lib.l2s_step_host(envs[r]._h, C.byref(io), acts.ctypes.data, host_out["pairs"].ctypes.data,
-                                      host_out["npairs"].ctypes.data, host_out["done"].ctypes.data,
-                                      host_out["rew"].ctypes.data, host_out["ms"].ctypes.data,
-                                      host_out["status"].ctypes.data, sp), "l2s_step_host")
+        _capi.check(lib.l2s_step_host(envs[r]._h, C.byref(io), acts.ctypes.data, None, None, None, None, None,
+                                      None, sp), "l2s_step_host")
+        return int(envs[r]._h_npairs[0]) + int(envs[r]._h_status[0])     # touch the host results
 
     for r, acts in hb[:w_e2e]:
         capi_step(r, acts)
@@ -314,7 +312,7 @@ def run_ours(args, rank, world, local_rank):
         capi_step(r, acts)
     torch.cuda.synchronize(dev)
     t_capi = time.perf_counter() - t0
-    assert not host_out["status"].any()
+    assert not any(e._h_status.any() for e in envs)
 
     # ---- phase 4: stateless evaluator (Evaluator.forward drop-in) on the current schedules ----------------
     from l2s_b200 import Evaluator
@@ -381,7 +379,7 @@ def run_ours(args, rank, world, local_rank):
                        "mean_pairs": pbar, "parallelism": "instance-sharded x%d" % world},
             "e2e": {"value": e2e_capi, "unit": UNIT,
                     "api": "C-ABI l2s_step_host: host int32 actions in, host pairs/npairs/done/reward/makespan/status out",
-                    "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": int(envs[0]._lib.l2s_pmax(envs[0]._h)) * B * 8 + B * 21,
+                    "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": int(envs[0]._lib.l2s_pmax(envs[0]._h)) * B * 4 + B * 21,
                     "steps": K},
             "e2e_python_api": {"value": e2e_py, "unit": UNIT,
                                "api": "drop-in JsspN5.step(actions: list[B][2], device) -> (state, reward, list[B][P][2], done); "

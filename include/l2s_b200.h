@@ -118,16 +118,18 @@ int l2s_step(l2s_handle h, const l2s_step_io* io, void* stream);
 
 /* Same step driven from HOST memory: copies `actions_host` ([batch,2] int32, may be NULL) to the device,
  * runs l2s_step with the device outputs in `io` (io->actions is ignored), copies the move sets back and
- * synchronises the stream.  Host outputs may be NULL.  pairs_host is [batch,pmax,2] int32. */
+ * synchronises the stream.  Host outputs may be NULL (read the pinned views of l2s_host_buffers instead).
+ * pairs_host is [batch,pmax,2] int32; only the first npairs_host[b] pairs of row b are written. */
 int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_host, int32_t* pairs_host,
                   int32_t* npairs_host, uint8_t* done_host, float* reward_host, float* makespan_host,
                   int32_t* status_host, void* stream);
 
 /* Pinned host buffers that l2s_step_host fills (zero-copy views for a binding; any out-pointer may be
- * NULL): pairs [batch,pmax,2], npairs/status [batch] int32, reward/makespan/incumbent [batch] float,
- * done [batch] uint8, and the pinned action staging buffer [batch,2] int32 (write actions there and pass
- * the same pointer as actions_host to skip a host copy). */
-int l2s_host_buffers(l2s_handle h, int32_t** pairs, int32_t** npairs, int32_t** status, float** reward,
+ * NULL): pairs16 [batch,pmax,2] uint16 (node ids fit 16 bits; only the first npairs[b] pairs of row b are
+ * defined), npairs/status [batch] int32, reward/makespan/incumbent [batch] float, done [batch] uint8, and the
+ * pinned action staging buffer [batch,2] int32 (write actions there and pass the same pointer as
+ * actions_host to skip a host copy). */
+int l2s_host_buffers(l2s_handle h, uint16_t** pairs16, int32_t** npairs, int32_t** status, float** reward,
                      float** makespan, float** incumbent, uint8_t** done, int32_t** actions);
 
 /* K fused steps in ONE launch with an on-device policy; the search state never leaves shared memory.

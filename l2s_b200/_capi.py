@@ -10,6 +10,7 @@ _lib = None
 c_i32p = C.POINTER(C.c_int32)
 c_f32p = C.POINTER(C.c_float)
 c_u8p = C.POINTER(C.c_uint8)
+c_u16p = C.POINTER(C.c_uint16)
 
 
 class L2SError(RuntimeError):
@@ -54,7 +55,7 @@ PROTOTYPES = {
     "l2s_step": (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p]),
     "l2s_step_host": (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "l2s_host_buffers": (C.c_int, [C.c_void_p, C.POINTER(c_i32p), C.POINTER(c_i32p), C.POINTER(c_i32p),
+    "l2s_host_buffers": (C.c_int, [C.c_void_p, C.POINTER(c_u16p), C.POINTER(c_i32p), C.POINTER(c_i32p),
                                    C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_u8p),
                                    C.POINTER(c_i32p)]),
     "l2s_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, c_i32p, C.c_int,

@@ -204,7 +204,7 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->off_ms = off;     off += ru(B * 4, 16);
   h->off_inc = off;    off += ru(B * 4, 16);
   h->off_done = off;   off += ru(B, 16);
-  h->off_pairs = off;  off += ru(B * pmax * 8, 16);
+  h->off_pairs = off;  off += ru(B * pmax * 4, 16);   // uint16 pairs
   h->pack_bytes = off;
   CU(cudaMalloc(&h->d_pack, h->pack_bytes));
   CU(cudaMemset(h->d_pack, 0, h->pack_bytes));
@@ -328,10 +328,10 @@ int l2s_step(l2s_handle h, const l2s_step_io* io, void* stream) {
   return r;
 }
 
-int l2s_host_buffers(l2s_handle h, int32_t** pairs, int32_t** npairs, int32_t** status, float** reward,
+int l2s_host_buffers(l2s_handle h, uint16_t** pairs16, int32_t** npairs, int32_t** status, float** reward,
                      float** makespan, float** incumbent, uint8_t** done, int32_t** actions) {
   if (!h) return L2S_ERR_INVALID_ARG;
-  if (pairs) *pairs = (int32_t*)(h->h_pack + h->off_pairs);
+  if (pairs16) *pairs16 = (uint16_t*)(h->h_pack + h->off_pairs);
   if (npairs) *npairs = (int32_t*)(h->h_pack + h->off_npairs);
   if (status) *status = (int32_t*)(h->h_pack + h->off_status);
   if (reward) *reward = (float*)(h->h_pack + h->off_reward);
@@ -358,7 +358,8 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
     a.actions = h->d_actions;
   }
   // results the host needs go to the packed block; per-instance scalars are mirrored there by the kernel
-  a.pairs = (int32_t*)(h->d_pack + h->off_pairs);
+  a.pairs = io->pairs;                                  // optional int32 device copy for the caller
+  a.pairs16 = (uint16_t*)(h->d_pack + h->off_pairs);    // packed copy that travels to the host
   a.npairs = (int32_t*)(h->d_pack + h->off_npairs);
   a.status = (int32_t*)(h->d_pack + h->off_status);
   a.reward2 = (float*)(h->d_pack + h->off_reward);
@@ -370,14 +371,20 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
   if (!io->is_reset && a.actions) h->itr += 1;
   CU(cudaMemcpyAsync(h->h_pack, h->d_pack, h->pack_bytes, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  if (pairs_host) memcpy(pairs_host, h->h_pack + h->off_pairs, B * h->pmax * 8);
+  if (pairs_host) {   // widen the packed uint16 pairs; only the valid prefix of every row is defined
+    const uint16_t* p16 = (const uint16_t*)(h->h_pack + h->off_pairs);
+    const int32_t* np = (const int32_t*)(h->h_pack + h->off_npairs);
+    for (size_t b = 0; b < B; ++b) {
+      const size_t row = b * (size_t)h->pmax * 2;
+      for (int i = 0; i < 2 * np[b]; ++i) pairs_host[row + i] = p16[row + i];
+    }
+  }
   if (npairs_host) memcpy(npairs_host, h->h_pack + h->off_npairs, B * 4);
   if (status_host) memcpy(status_host, h->h_pack + h->off_status, B * 4);
   if (reward_host) memcpy(reward_host, h->h_pack + h->off_reward, B * 4);
   if (makespan_host) memcpy(makespan_host, h->h_pack + h->off_ms, B * 4);
   if (done_host) memcpy(done_host, h->h_pack + h->off_done, B);
   // device copies requested by the caller in io (rare: the host path normally leaves these NULL)
-  if (io->pairs) CU(cudaMemcpyAsync(io->pairs, a.pairs, B * h->pmax * 8, cudaMemcpyDeviceToDevice, s));
   if (io->npairs) CU(cudaMemcpyAsync(io->npairs, a.npairs, B * 4, cudaMemcpyDeviceToDevice, s));
   if (io->status) CU(cudaMemcpyAsync(io->status, a.status, B * 4, cudaMemcpyDeviceToDevice, s));
   return L2S_OK;

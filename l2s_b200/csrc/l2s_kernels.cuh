@@ -283,6 +283,7 @@ struct StepArgs {
   float* reward;
   uint8_t* done;
   int32_t* pairs;
+  uint16_t* pairs16;       // packed host-path copy of the pair list: uint16 [B][pmax][2]
   int32_t* npairs;
   int32_t* status;
   int pmax;
@@ -442,11 +443,15 @@ __global__ void __launch_bounds__(128, 10) step_kernel(const __grid_constant__ S
     if (lane == 0) a.ex_path_len[b] = len;
   }
   int32_t* po = a.pairs ? a.pairs + (size_t)b * a.pmax * 2 : nullptr;
+  uint32_t* po16 = a.pairs16 ? reinterpret_cast<uint32_t*>(a.pairs16) + (size_t)b * a.pmax : nullptr;
   const int pmax = a.pmax;
   int np = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
-    if (po && idx < pmax) {
-      po[2 * idx] = u;
-      po[2 * idx + 1] = v;
+    if (idx < pmax) {
+      if (po) {
+        po[2 * idx] = u;
+        po[2 * idx + 1] = v;
+      }
+      if (po16) po16[idx] = (uint32_t)u | ((uint32_t)v << 16);
     }
   });
   if (np < 0) { status = status ? status : np; np = 0; }

@@ -119,11 +119,11 @@ class JsspN5:
             _capi.check(self._lib.l2s_create(self.n_job, self.n_mch, B, self.pmax, device.index, C.byref(h)),
                         "l2s_create")
             self._h, self._key, self._device = h, key, device
-            p = [_capi.c_i32p(), _capi.c_i32p(), _capi.c_i32p(), _capi.c_f32p(), _capi.c_f32p(), _capi.c_f32p(),
+            p = [_capi.c_u16p(), _capi.c_i32p(), _capi.c_i32p(), _capi.c_f32p(), _capi.c_f32p(), _capi.c_f32p(),
                  _capi.c_u8p(), _capi.c_i32p()]
             _capi.check(self._lib.l2s_host_buffers(h, *[C.byref(q) for q in p]), "l2s_host_buffers")
             pm = self._lib.l2s_pmax(h)
-            self._h_pairs = _np_view(p[0], (B, pm, 2), np.int32)
+            self._h_pairs = _np_view(p[0], (B, pm, 2), np.uint16)
             self._h_npairs = _np_view(p[1], (B,), np.int32)
             self._h_status = _np_view(p[2], (B,), np.int32)
             self._h_actions = _np_view(p[7], (B, 2), np.int32)
