@@ -232,6 +232,53 @@ class JsspN5:
         self._poll("export_state")
         return dict(est=est, lst=lst, path=path, path_len=plen, tabu=tabu, jobfirst=jf, makespan=ms, incumbent=inc)
 
+    # -- device-tensor interface: no host round trip per step ---------------------------------
+    def reset_device(self, instances, init_type, device, init_solutions=None):
+        """Like `reset`, but the move sets stay on the GPU: returns (state, pairs int32 [B,pmax,2],
+        npairs int32 [B], done bool [B,1]).  Pair rows are valid up to npairs[b]."""
+        self.reset(instances, init_type, device, init_solutions=init_solutions)
+        state, _, pairs, npairs, done = self._launch_device(None, is_reset=True)
+        return state, pairs, npairs, done
+
+    def step_device(self, actions):
+        """actions: int32 device tensor [B,2] ((0,0) = dummy).  One kernel launch, nothing is copied to the
+        host and nothing synchronises; call `check_errors()` whenever convenient (e.g. every few hundred steps).
+        Returns (state, reward [B,1], pairs int32 [B,pmax,2], npairs int32 [B], done bool [B,1])."""
+        if self.reward_type not in _capi.REWARD:
+            raise ValueError('reward type must be "yaoxin" or "consecutive".')
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.shape == (self._key[0], 2)
+        out = self._launch_device(actions.contiguous(), is_reset=False)
+        self.itr = self.itr + 1
+        return out
+
+    def check_errors(self):
+        """Synchronise and raise if any instance reported a device-side error since the last check."""
+        self._poll("step_device")
+
+    def _launch_device(self, actions, is_reset):
+        B, device = self._key[0], self._device
+        n1 = self.n_oprs + 2
+        e_mc = self.n_mch * (self.n_job - 1)
+        pm = self._h_pairs.shape[1]
+        x = torch.empty((B * n1, 3), dtype=torch.float32, device=device)
+        emc = torch.empty((2, B * e_mc), dtype=torch.int64, device=device)
+        ms = torch.empty((B, 1), dtype=torch.float32, device=device)
+        inc = torch.empty((B, 1), dtype=torch.float32, device=device)
+        reward = torch.empty((B, 1), dtype=torch.float32, device=device)
+        done = torch.empty((B, 1), dtype=torch.bool, device=device)
+        pairs = torch.empty((B, pm, 2), dtype=torch.int32, device=device)
+        npairs = torch.empty((B,), dtype=torch.int32, device=device)
+        io = StepIO(actions=actions.data_ptr() if actions is not None else None, high=float(self.high),
+                    fea_norm_const=float(self.fea_norm_const), reward_type=_capi.REWARD.get(self.reward_type, 0),
+                    is_reset=1 if is_reset else 0, x=x.data_ptr(), edge_index_mc=emc.data_ptr(), makespan=ms.data_ptr(),
+                    incumbent=inc.data_ptr(), reward=reward.data_ptr(), done=done.data_ptr(), pairs=pairs.data_ptr(),
+                    npairs=npairs.data_ptr(), status=None)
+        _capi.check(self._lib.l2s_step(self._h, C.byref(io), _stream_ptr(device)), "l2s_step")
+        self.current_objs, self.incumbent_objs = ms, inc
+        state = (x, self._const[0], emc, self._const[1])
+        self._last_device = (state, pairs, npairs, done)
+        return state, reward, pairs, npairs, done
+
     # -- fused rollouts (no host round trip inside the loop) -------------------------------------------
     def run(self, policy, steps, tape=None, seed=0, log_steps=(), return_actions=False):
         """K = `steps` fused steps in ONE launch with an on-device policy ('replay' with tape [B,K,2],
