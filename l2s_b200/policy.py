@@ -181,11 +181,12 @@ class Actor(nn.Module):
         (actions int32 [B, 2] with (0,0) where an instance has no move, log_prob float [B, 1])."""
         B, P = pairs.shape[0], pairs.shape[1]
         h = self.node_features(x, edge_index_pc, edge_index_mc, B)               # [B, n1, H]
-        idx = pairs.long().clamp(min=0)
+        valid = torch.arange(P, device=x.device).unsqueeze(0) < npairs.unsqueeze(1)
+        pairs = torch.where(valid.unsqueeze(-1), pairs, torch.zeros_like(pairs))   # rows are defined up to npairs[b]
+        idx = pairs.long()
         ha = torch.gather(h, 1, idx[:, :, 0:1].expand(B, P, h.shape[-1]))
         hb = torch.gather(h, 1, idx[:, :, 1:2].expand(B, P, h.shape[-1]))
         score = (ha * hb).sum(-1)                                                # [B, P] = bmm(h, h^T)[b, a0, a1]
-        valid = torch.arange(P, device=x.device).unsqueeze(0) < npairs.unsqueeze(1)
         has = npairs > 0
         score = score.masked_fill(~valid, -float("inf"))
         score = torch.where(has.unsqueeze(1), score, torch.zeros_like(score))    # no move: uniform dummy row
