@@ -152,6 +152,23 @@ def run_reference(args, rank, world):
     rate = cpu_port_rate(n_j, n_m, per * procs, max(1, args.steps), max(0, min(args.warmup, 3)), procs)
     wall = time.perf_counter() - t0
     units = per * procs * args.steps
+    # additionally: the plain-C restatement (oracle/l2s_oracle.c) on all cores -- the strongest CPU number we have
+    c_port = None
+    try:
+        from oracle import c_oracle as CO
+        cb = 64 * procs if n_j * n_m <= 400 else 4 * procs
+        inst = gen_instances(n_j, n_m, cb, 5)
+        mseq = np.stack([CO.rules_solver(i[0], i[1])[0] for i in inst])
+        cenv = CO.CEnv(inst, mseq, threads=procs)
+        cenv.run("random", 5, seed=1, write_state=True, return_actions=False)
+        ksteps = 50 if n_j * n_m <= 400 else 10
+        t1 = time.perf_counter()
+        cenv.run("random", ksteps, seed=2, write_state=True, return_actions=False)
+        c_port = {"value": cb * ksteps / (time.perf_counter() - t1), "unit": UNIT, "threads": procs,
+                  "what": "oracle/l2s_oracle.c orc_run_batch (OpenMP): per step swap + O(n) topological evaluation + "
+                          "features + machine edges + critical path + N5 pairs, %d instances x %d steps" % (cb, ksteps)}
+    except Exception as e:   # the C oracle is optional for this line
+        c_port = {"error": str(e)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * units / rate / args.steps,
@@ -163,7 +180,7 @@ def run_reference(args, rank, world):
                                    "(oracle/l2s_oracle.py OracleEnv.step); the reference itself is pure Python "
                                    "(networkx + torch CPU) and cannot travel to this box" % (procs, per, args.steps)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": wall,
+        "gpu_launches": 0, "wall_s": wall, "c_port": c_port,
     }
     print(json.dumps(line), flush=True)
 
@@ -336,13 +353,31 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_ev = e0.elapsed_time(e1)
     assert torch.equal(mk.reshape(-1), envs[(k_ev - 1) % REPLICAS].current_objs.reshape(-1))
+
+    # ---- phase 5: fused K-step search (l2s_run): on-device policy, state resident in shared memory ------------
+    k_f = max(10, min(K, 100))
+    envs[0].run("random", 5, seed=11)
+    barrier()
+    e0.record(stream)
+    for r in range(REPLICAS):
+        envs[r].run("random", k_f, seed=12 + r)
+    e1.record(stream)
+    barrier()
+    ms_fused = e0.elapsed_time(e1)
+    k_g = max(2, min(K, 10))
+    barrier()
+    e0.record(stream)
+    envs[0].run("greedy", k_g)
+    e1.record(stream)
+    barrier()
+    ms_greedy = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
-    times = torch.tensor([ms_dev / 1e3, t_py, t_capi, ms_ev / 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_dev / 1e3, t_py, t_capi, ms_ev / 1e3, ms_fused / 1e3, ms_greedy / 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_py, t_capi, t_ev = [float(v) for v in times.cpu()]
+    t_dev, t_py, t_capi, t_ev, t_fused, t_greedy = [float(v) for v in times.cpu()]
     value = world * B * K / t_dev
     e2e_py = world * B * k_e2e / t_py
     e2e_capi = world * B * K / t_capi
@@ -390,6 +425,10 @@ def run_ours(args, rank, world, local_rank):
                           "algorithmic_bytes_per_graph": 8 * n1 + 16 * (n_j * (n_m + 1) + e_mc) + 8 * n1 + 4,
                           "achieved_gbs": (8 * n1 + 16 * (n_j * (n_m + 1) + e_mc) + 8 * n1 + 4) * B * k_ev / t_ev / 1e9 / 1.0,
                           "frac_of_peak": (8 * n1 + 16 * (n_j * (n_m + 1) + e_mc) + 8 * n1 + 4) * B * k_ev / t_ev / 1e9 / peak},
+            "fused_run": {"random_policy_inst_steps_per_s": world * B * k_f * REPLICAS / t_fused,
+                          "greedy_policy_inst_steps_per_s": world * B * k_g / t_greedy,
+                          "api": "l2s_run: K steps per launch, on-device policy, no host round trip, no x/edge outputs",
+                          "steps_per_launch": k_f},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "l2s::step_kernel",
