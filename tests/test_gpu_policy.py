@@ -58,3 +58,38 @@ def test_learned_rollout_gap_matches_reference_statistics():
     assert 0.02 < gap < 0.07, "mean gap %.4f outside the plausible range around the reference's 0.0444" % gap
     res_l, _ = rollout(inst[:20], os.path.join(POL, "incumbent_10x10_gin+dghan.pth"), 60, mode="lists")
     assert (res_l[60] >= opt[:20] - 1e-6).all()
+
+
+def test_reinforce_loss_matches_reference_formula_and_training_runs():
+    """The vectorised n-step REINFORCE loss equals the reference's per-instance loop
+    (n-step_reinforce.py:40-59); two gradient batches run end to end on the GPU env."""
+    from l2s_b200 import JsspN5
+    from l2s_b200.policy import Actor
+    from l2s_b200.training import reinforce_loss, train_batch
+    torch.manual_seed(0)
+    B, n = 7, 10
+    rewards = [torch.rand(B, 1, device="cuda") for _ in range(n)]
+    logps = [torch.randn(B, 1, device="cuda", requires_grad=True) for _ in range(n)]
+    dones = [(torch.rand(B, 1, device="cuda") < 0.2) for _ in range(n)]
+    dones[0][:] = False
+    got = reinforce_loss(rewards, logps, dones, gamma=1.0)
+    R = torch.zeros_like(rewards[0])
+    rets = []
+    for r in rewards[::-1]:
+        R = r + R
+        rets.insert(0, R)
+    rets, dn, lp = torch.cat(rets, -1), torch.cat(dones, -1), torch.cat(logps, -1)
+    losses = []
+    for b in range(B):
+        mR = torch.masked_select(rets[b], ~dn[b])
+        mR = (mR - mR.mean()) / (torch.std(mR, unbiased=False) + np.finfo(np.float32).eps.item())
+        losses.append((-torch.masked_select(lp[b], ~dn[b]) * mR).sum())
+    assert torch.allclose(got, torch.stack(losses).mean(), rtol=1e-4, atol=1e-5)
+    policy = Actor(3, 64, embedding_l=2, policy_l=2, embedding_type='gin+dghan', heads=1, dropout=0.0).cuda()
+    opt = torch.optim.Adam(policy.parameters(), lr=1e-4)
+    before = torch.cat([p.detach().reshape(-1).clone() for p in policy.parameters()])
+    inst = np.load(os.path.join(POL, "syn10x10.npy"))[:8]
+    inc, cur, n_upd = train_batch(policy, opt, JsspN5(10, 10, 1, 99), inst, transit=30, steps_learn=10)
+    after = torch.cat([p.detach().reshape(-1) for p in policy.parameters()])
+    assert n_upd == 3 and not torch.equal(before, after) and torch.isfinite(after).all()
+    assert (inc <= cur + 1e-6).all()
