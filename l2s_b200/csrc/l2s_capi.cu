@@ -166,7 +166,7 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
     I.off_pri = off;    off += ru((long long)n_j * 8, 16);
     I.bytes = off;
   }
-  h->warps_step = pick_warps(L.bytes, 4);   // step_kernel is compiled with __launch_bounds__(128, 10)
+  h->warps_step = pick_warps(L.bytes, 4);   // step_kernel is compiled with __launch_bounds__(128, 8)
   if (const char* e = getenv("L2S_WARPS_STEP")) { int v = atoi(e); if (v > 0 && v <= 4 && (size_t)v * L.bytes <= kSmemPerCtaMax) h->warps_step = v; }
   h->warps_run = pick_warps(h->run_stride);
   h->warps_init = pick_warps(h->IL.bytes);
