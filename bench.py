@@ -333,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- phase 4: stateless evaluator (Evaluator.forward drop-in) on the current schedules ----------------
     from l2s_b200 import Evaluator
-    ev = Evaluator()
+    ev = Evaluator(strict=False)      # asynchronous calls; the status word is checked once after the loop
     ev_in = []
     for r in range(REPLICAS):
         state, fa, done = envs[r].observe()
@@ -352,6 +352,7 @@ def run_ours(args, rank, world, local_rank):
     e1.record(stream)
     barrier()
     ms_ev = e0.elapsed_time(e1)
+    ev.check()
     assert torch.equal(mk.reshape(-1), envs[(k_ev - 1) % REPLICAS].current_objs.reshape(-1))
 
     # ---- phase 5: fused K-step search (l2s_run): on-device policy, state resident in shared memory ------------

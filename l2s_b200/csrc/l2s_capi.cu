@@ -520,9 +520,9 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   g.magic_n1 = (unsigned)((1ull << 32) / (unsigned)(n + 2)) + 1u;
   g.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   g.ws = a.ws;
-  long long blocks = (n_edges + 4 * 1024 - 1) / (4 * 1024);   // ~4 edges per thread
+  long long blocks = (n_edges + 8 * 512 - 1) / (8 * 512);   // ~8 edges per thread (two 2-edge vector trips x2)
   if (blocks < 1) blocks = 1;
-  coo_ingest_kernel<<<(unsigned)blocks, 1024, 0, s>>>(g);
+  coo_ingest_kernel<<<(unsigned)blocks, 512, 0, s>>>(g);
   CU(cudaGetLastError());
   coo_eval_kernel<<<(unsigned)((batch + W - 1) / W), W * 32, (size_t)W * a.bytes, s>>>(a);
   CU(cudaGetLastError());

@@ -14,10 +14,23 @@ from ._capi import L2SError
 
 
 class Evaluator:
-    def __init__(self):
+    """`strict=True` (default) reads the device status word back after every call and raises on malformed input
+    (one 4-byte D2H + sync; the reference synchronises 2*depth times per call).  `strict=False` keeps the call
+    fully asynchronous like any CUDA op; call `check()` when convenient to surface a recorded error."""
+
+    def __init__(self, strict=True):
         self._lib = _capi.lib()
         self._ws = None
         self._flag = None
+        self._sticky = None
+        self.strict = strict
+
+    def check(self):
+        if self._sticky is not None:
+            flag = int(self._sticky.item())
+            self._sticky.zero_()
+            if flag < 0:
+                raise L2SError(flag, "Evaluator.forward")
 
     def forward(self, edge_index, duration, n_j, n_m):
         if not edge_index.is_cuda or not duration.is_cuda:
@@ -39,6 +52,7 @@ class Evaluator:
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
             self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+            self._sticky = torch.zeros(1, dtype=torch.int32, device=device)
         est = torch.empty((N, 1), dtype=torch.float32, device=device)
         lst = torch.empty((N, 1), dtype=torch.float32, device=device)
         ms = torch.empty((B, 1), dtype=torch.float32, device=device)
@@ -48,7 +62,10 @@ class Evaluator:
             n_j, n_m, B, C.c_void_p(est.data_ptr()), C.c_void_p(lst.data_ptr()), C.c_void_p(ms.data_ptr()),
             C.c_void_p(self._ws.data_ptr()), self._ws.numel(), C.c_void_p(self._flag.data_ptr()),
             device.index if device.index is not None else torch.cuda.current_device(), stream), "l2s_eval_coo")
-        flag = int(self._flag.item())   # the reference synchronises 2*depth times per call; we do it once
-        if flag < 0:
-            raise L2SError(flag, "Evaluator.forward")
+        if self.strict:
+            flag = int(self._flag.item())   # the reference synchronises 2*depth times per call; we do it once
+            if flag < 0:
+                raise L2SError(flag, "Evaluator.forward")
+        else:
+            torch.minimum(self._sticky, self._flag, out=self._sticky)   # keep the most recent error for check()
         return est, lst, ms
