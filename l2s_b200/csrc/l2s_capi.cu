@@ -100,6 +100,7 @@ struct l2s_handle_s {
   long long inst_off;
   long long itr;
   int warps_step, warps_run, warps_init;
+  int cta_warps;   // > 0: large instances -> step_kernel_cta with this many warps per instance
   size_t run_stride;
   int run_off_where, run_off_plist;
   InitLayout IL;
@@ -171,6 +172,15 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->warps_run = pick_warps(h->run_stride);
   h->warps_init = pick_warps(h->IL.bytes);
   if (!h->warps_step || !h->warps_run || !h->warps_init) { free(h); return L2S_ERR_UNSUPPORTED_SHAPE; }
+  // few instances per SM (large graphs): give every instance a whole CTA so that the SM is not left idle
+  {
+    const long long per_sm = (long long)(kSmemPerSm / ((size_t)L.bytes + kSmemCtaReserve));
+    h->cta_warps = per_sm < 16 ? (per_sm <= 8 ? 8 : 4) : 0;   // measured: 100x20/150x25 best at 8, 50x20 at 4, 30x20 warp-per-instance
+    if (const char* e = getenv("L2S_CTA_WARPS")) h->cta_warps = atoi(e);
+    if (h->cta_warps > 8) h->cta_warps = 8;
+  }
+  CU(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax - 1024));   // it also has static shared memory
+  CU(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CU(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
   CU(cudaFuncSetAttribute(run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
   CU(cudaFuncSetAttribute(build_initial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
@@ -278,6 +288,11 @@ int l2s_build_initial(l2s_handle h, int rule, int high, void* stream) {
 }
 
 static int launch_step(l2s_handle h, const StepArgs& a, void* stream) {
+  if (h->cta_warps > 0) {
+    step_kernel_cta<<<h->B, h->cta_warps * 32, (size_t)h->L.bytes, (cudaStream_t)stream>>>(a);
+    CU(cudaGetLastError());
+    return L2S_OK;
+  }
   const int W = h->warps_step;
   step_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * h->L.bytes, (cudaStream_t)stream>>>(a);
   CU(cudaGetLastError());

@@ -123,20 +123,20 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ __forceinline__ void fill_pending(const Layout& L, const Inst& s, int lane, bool fill_q) {
+__device__ __forceinline__ void fill_pending(const Layout& L, const Inst& s, int lane, bool fill_q, int nthr = 32) {
   const uint4 pending = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   const int cnt = (fill_q ? 2 : 1) * (L.n1p / 4);
-  for (int i = lane; i < cnt; i += 32) sts128(s.tq + 16 * i, pending);
+  for (int i = lane; i < cnt; i += nthr) sts128(s.tq + 16 * i, pending);
 }
 
 // Coalesced 16-byte staging of one instance's state into shared memory + sentinel fill of tq.
 __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, const State& st, int b, int lane,
-                                               bool fill_q) {
+                                               bool fill_q, int nthr = 32) {
   const uint4* gd = reinterpret_cast<const uint4*>(st.durw + (size_t)b * L.node_stride);
   const uint4* gw = reinterpret_cast<const uint4*>(st.walk + (size_t)b * L.walk_stride);
-  for (int i = lane; i < L.node_stride / 8; i += 32) sts128(s.durw + 16 * i, ld_nc16(gd + i));   // static
-  for (int i = lane; i < L.walk_stride / 4; i += 32) sts128(s.walk + 16 * i, gw[i]);
-  fill_pending(L, s, lane, fill_q);
+  for (int i = lane; i < L.node_stride / 8; i += nthr) sts128(s.durw + 16 * i, ld_nc16(gd + i));   // static
+  for (int i = lane; i < L.walk_stride / 4; i += nthr) sts128(s.walk + 16 * i, gw[i]);
+  fill_pending(L, s, lane, fill_q, nthr);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -237,8 +237,8 @@ __device__ __forceinline__ int evaluate_instance(const Layout& L, const Inst& s,
 //             if there is no other predecessor) -- this is what nx.dag_longest_path keeps per node;
 //   msu[v]  = its machine successor (0 = none), if want_msu.
 template <bool want_msu>
-__device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, int lane) {
-  for (int i = lane; i < L.n; i += 32) {
+__device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, int lane, int nthr = 32) {
+  for (int i = lane; i < L.n; i += nthr) {
     const unsigned w = (unsigned)lds32(s.walk + 4u * i);
     const unsigned wp = i > 0 ? (unsigned)lds32(s.walk + 4u * (i - 1)) : kWRowEnd;
     const unsigned v = w & kWId;

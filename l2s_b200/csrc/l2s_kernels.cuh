@@ -487,6 +487,201 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
 }
 
 // ------------------------------------------------------------------------------------------------------
+// The same step for LARGE instances (few instances fit an SM, so one warp per instance would leave the SM
+// almost empty): one CTA of kW warps owns one instance.  Warp 0 runs the forward sweep while warp 1 runs the
+// backward sweep; staging, the link pass and the x / edge outputs are spread over all threads; the critical
+// path trace and the move enumeration stay on warp 0.  Synchronisation is __syncthreads (one instance per CTA).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_step[];
+  __shared__ int sh[8];   // 0: i0, 1: swap result, 2: has_t, 3: ms, 4: fwd ok, 5: bwd ok, 6: qs, 7: scratch
+  __shared__ int wcount[8];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+  const int b = blockIdx.x;
+  const Layout& L = a.L;
+  const Inst s = inst_view(L, smem_addr(smem_step));
+  const int n = L.n, n1 = L.n1;
+
+  int a0 = 0, a1 = 0;
+  if (a.actions && !a.export_only) {
+    a0 = a.actions[2 * b];
+    a1 = a.actions[2 * b + 1];
+  }
+  int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
+  if (tid < 8) sh[tid] = tid == 0 ? -1 : 0;
+  stage_instance(L, s, a.st, b, tid, true, nthr);
+  __syncthreads();
+  if (a0 >= 1 && a0 <= n) {
+    int i0 = -1;
+    for (int i = tid; i < n; i += nthr)
+      if ((lds32(s.walk + 4u * i) & (int)kWId) == a0) i0 = i;
+    if (i0 >= 0) sh[0] = i0;     // a node id occurs exactly once
+  }
+  __syncthreads();
+  const int i0 = sh[0];
+  int status = 0;
+  if (w == 0) {
+    bool has_t = false;
+    const int r = apply_swap(L, s, a0, a1, i0, lane, has_t);
+    if (lane == 0) { sh[1] = r; sh[2] = has_t; }
+    if (r == 0 && lane == 0) {
+      uint32_t* gw = a.st.walk + (size_t)b * L.walk_stride;
+      gw[i0] = (uint32_t)lds32(s.walk + 4u * i0);
+      gw[i0 + 1] = (uint32_t)lds32(s.walk + 4u * (i0 + 1));
+      if (has_t) gw[i0 + 2] = (uint32_t)lds32(s.walk + 4u * (i0 + 2));
+      a.st.tabu[2 * b] = a1;
+      a.st.tabu[2 * b + 1] = a0;
+    }
+  }
+  __syncthreads();
+  {
+    const int r = sh[1];
+    if (r == 0) { tabu0 = a1; tabu1 = a0; } else if (r < 0) status = r;
+  }
+  // evaluation: forward sweep on warp 0, backward sweep on warp 1 (or both on warp 0 if the CTA has one warp)
+  if (w == 0) {
+    int last;
+    const bool ok = wavefront(L, s, lane, 0, lane < L.n_m, last);
+    const int ms0 = __reduce_max_sync(kFull, last);
+    if (lane == 0) { sh[3] = ms0; sh[4] = ok; }
+    if (nw == 1) {
+      int l2;
+      const bool ok2 = wavefront(L, s, lane, 1, lane < L.n_m, l2);
+      if (lane == 0) sh[5] = ok2;
+    }
+  } else if (w == 1) {
+    int l2;
+    const bool ok2 = wavefront(L, s, lane, 1, lane < L.n_m, l2);
+    if (lane == 0) sh[5] = ok2;
+  }
+  __syncthreads();
+  const int ms = sh[3];
+  if (!sh[4] || !sh[5]) {
+    if (tid == 0) {
+      record_error(a.st.err, -5, b);
+      if (a.status) a.status[b] = -5;
+      if (a.npairs) a.npairs[b] = 0;
+      if (a.done) a.done[b] = 1;
+      if (a.done2) a.done2[b] = 1;
+    }
+    return;
+  }
+  if (a.emc) link_pass<true>(L, s, tid, nthr); else link_pass<false>(L, s, tid, nthr);
+  const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
+  {
+    int qs = 0;
+    for (int j = tid; j < L.n_j; j += nthr) qs = max(qs, lds32(q + 4u * (j * L.n_m + 1)));
+    qs = __reduce_max_sync(kFull, qs);
+    if (lane == 0 && qs > 0) atomicMax(&sh[6], qs);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    sts32(fin, 0);
+    sts32(q, sh[6]);
+    sts32(fin + 4u * (n + 1), ms);
+    sts32(q + 4u * (n + 1), 0);
+  }
+  __syncthreads();
+  if (a.x) {
+    float* xo = a.x + (size_t)b * n1 * 3;
+    const float fms = (float)ms;
+    for (int i = tid; i < n1; i += nthr) {
+      const int d = lds16(s.durw + 2u * i) & kDurMask;
+      const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
+      xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
+      xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
+      xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
+    }
+  }
+  if (a.ex_est) {
+    for (int i = tid; i < n1; i += nthr) {
+      const int d = lds16(s.durw + 2u * i) & kDurMask;
+      a.ex_est[(size_t)b * n1 + i] = lds32(fin + 4u * i) - d;
+      a.ex_lst[(size_t)b * n1 + i] = ms - lds32(q + 4u * i);
+    }
+  }
+  if (a.emc) {
+    // ordered compaction over contiguous node chunks, one per warp: count, exchange, write
+    const int chunk = ((n + nw - 1) / nw + 31) & ~31;
+    const int vlo = 1 + w * chunk, vhi = min(n, vlo + chunk - 1);
+    int cnt = 0;
+    for (int v0 = vlo; v0 <= vhi; v0 += 32) {
+      const int v = v0 + lane;
+      cnt += __popc(__ballot_sync(kFull, v <= vhi && lds16(s.msu + 2u * v) != 0));
+    }
+    if (lane == 0) wcount[w] = cnt;
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < w; ++k) base += wcount[k];
+    const unsigned off = (unsigned)b * (unsigned)n1;
+    uint2* src = reinterpret_cast<uint2*>(a.emc) + (size_t)b * L.e_mc + base;
+    uint2* dst = src + (size_t)a.B * L.e_mc;
+    const unsigned below = (1u << lane) - 1u;
+    for (int v0 = vlo; v0 <= vhi; v0 += 32) {
+      const int v = v0 + lane;
+      const unsigned sc = v <= vhi ? (unsigned)lds16(s.msu + 2u * v) : 0u;
+      const unsigned bal = __ballot_sync(kFull, sc != 0u);
+      if (sc) {
+        const int pos = __popc(bal & below);
+        src[pos] = make_uint2(off + (unsigned)v, 0u);
+        dst[pos] = make_uint2(off + sc, 0u);
+      }
+      const int adv = __popc(bal);
+      src += adv;
+      dst += adv;
+    }
+  }
+  __syncthreads();   // q is dead from here on: its storage becomes the reversed critical path
+  if (w != 0) return;
+  const uint32_t rp = q;
+  const int len = trace_path(L, s, ms, lane, rp);
+  if (a.ex_path) {
+    for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = lds16(rp + 2u * (len - 1 - i));
+    if (lane == 0) a.ex_path_len[b] = len;
+  }
+  int32_t* po = a.pairs ? a.pairs + (size_t)b * a.pmax * 2 : nullptr;
+  uint32_t* po16 = a.pairs16 ? reinterpret_cast<uint32_t*>(a.pairs16) + (size_t)b * a.pmax : nullptr;
+  const int pmax = a.pmax;
+  int np = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
+    if (idx < pmax) {
+      if (po) {
+        po[2 * idx] = u;
+        po[2 * idx + 1] = v;
+      }
+      if (po16) po16[idx] = (uint32_t)u | ((uint32_t)v << 16);
+    }
+  });
+  if (np < 0) { status = status ? status : np; np = 0; }
+  if (np > pmax) { status = status ? status : -8; np = pmax; }
+  if (lane == 0) {
+    const int inc_old = a.st.inc[b], cur_old = a.st.cur[b];
+    int reward, inc;
+    if (a.is_reset) {
+      reward = 0;
+      inc = ms;
+    } else {
+      reward = a.reward_type == 1 ? cur_old - ms : max(inc_old - ms, 0);
+      inc = min(inc_old, ms);
+    }
+    if (!a.export_only) {
+      a.st.cur[b] = ms;
+      a.st.inc[b] = inc;
+    }
+    if (a.makespan) a.makespan[b] = (float)ms;
+    if (a.incumbent) a.incumbent[b] = (float)inc;
+    if (a.reward) a.reward[b] = (float)reward;
+    if (a.done) a.done[b] = np == 0;
+    if (a.makespan2) a.makespan2[b] = (float)ms;
+    if (a.incumbent2) a.incumbent2[b] = (float)inc;
+    if (a.reward2) a.reward2[b] = (float)reward;
+    if (a.done2) a.done2[b] = np == 0;
+    if (a.npairs) a.npairs[b] = np;
+    if (a.status) a.status[b] = status;
+    if (status) record_error(a.st.err, status, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // K fused steps with an on-device policy; state stays in shared memory for the whole launch.
 // ------------------------------------------------------------------------------------------------------
 constexpr int kMaxLog = 16;
