@@ -44,9 +44,16 @@ Layout make_layout(int n_j, int n_m) {
   int off = 0;
   L.off_tq = off;   off += 2 * L.n1p * 4;
   L.off_walk = off; off += L.walk_stride * 4;
-  L.off_durw = off; off += L.node_stride * 2;
-  L.off_aux = off;  off += 2 * L.node_stride * 2;
+  L.off_crit = off; off += L.node_stride * 2;
   L.off_misc = off; off += 16;
+  // small instances keep the static node words in shared memory too (cheaper feature loop); large ones read them
+  // from HBM so that one more instance fits an SM
+  L.off_durw = -1;
+  if ((size_t)ru(off, 16) + (size_t)L.node_stride * 2 + kSmemCtaReserve <= kSmemPerSm / 16) {
+    L.off_durw = off;
+    off += L.node_stride * 2;
+  }
+  L.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   L.bytes = ru(off, 16);
   return L;
 }
@@ -513,8 +520,9 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   a.ws.flag = status_flag;
   a.est = est; a.lst = lst; a.ms = makespan;
   a.expect_conj = batch * ((long long)n_j * (n_m + 1));
-  // shared memory: tq | walk | durw (offsets of the env layout), then successors and the head list
-  int off = L.off_aux;
+  // shared memory: tq | walk (offsets of the env layout), then node words, successors and the head list
+  int off = L.off_crit;
+  a.off_durw = off;  off += L.node_stride * 2;
   a.off_succ = off;  off += L.node_stride * 2;
   a.off_heads = off; off += 64;
   a.bytes = ru(off, 16);

@@ -56,7 +56,9 @@ struct Layout {
   int node_stride;       // uint16 elements per instance of node-indexed arrays (multiple of 8, >= n1)
   int mch_stride;        // bytes per instance of the machine-id array (multiple of 16)
   int e_mc;              // machine edges per instance n_m*(n_j-1)
-  int off_tq, off_walk, off_durw, off_aux, off_misc;   // aux = uint16 [2][node_stride]: critical predecessor | machine successor
+  int off_tq, off_walk, off_crit, off_misc;
+  int off_durw;          // >= 0: static node words staged in shared memory (small instances); -1: read from HBM
+  unsigned magic_nm;     // floor(2^32 / n_m) + 1: (x mod n_m) by multiply-shift for x < 2^16
   int bytes;             // per instance (step kernel)
 };
 
@@ -92,9 +94,8 @@ __device__ __forceinline__ void sts16(uint32_t a, int v) {
 struct Inst {            // shared-memory view of one instance (32-bit shared addresses)
   uint32_t tq;           // int32 [2][n1p]: [v] = est[v]+dur[v] ("fin"), [n1p+v] = tail q[v]; -1 = pending
   uint32_t walk;         // uint32 [walk_stride]
-  uint32_t durw;         // uint16 [node_stride]
   uint32_t crit;         // uint16 [node_stride] chosen critical predecessor (networkx tie-break); 0 = S
-  uint32_t msu;          // uint16 [node_stride] machine successor of every node (0 = none), by the backward sweep
+  uint32_t durw;         // uint16 [node_stride] node words, valid iff Layout::off_durw >= 0
   uint32_t misc;         // int32 [4] parked scalars
 };
 
@@ -102,9 +103,8 @@ __device__ __forceinline__ Inst inst_view(const Layout& L, uint32_t base) {
   Inst s;
   s.tq = base + L.off_tq;
   s.walk = base + L.off_walk;
-  s.durw = base + L.off_durw;
-  s.crit = base + L.off_aux;
-  s.msu = s.crit + 2u * L.node_stride;
+  s.crit = base + L.off_crit;
+  s.durw = base + (L.off_durw >= 0 ? L.off_durw : 0);
   s.misc = base + L.off_misc;
   return s;
 }
@@ -132,10 +132,12 @@ __device__ __forceinline__ void fill_pending(const Layout& L, const Inst& s, int
 // Coalesced 16-byte staging of one instance's state into shared memory + sentinel fill of tq.
 __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, const State& st, int b, int lane,
                                                bool fill_q, int nthr = 32) {
-  const uint4* gd = reinterpret_cast<const uint4*>(st.durw + (size_t)b * L.node_stride);
   const uint4* gw = reinterpret_cast<const uint4*>(st.walk + (size_t)b * L.walk_stride);
-  for (int i = lane; i < L.node_stride / 8; i += nthr) sts128(s.durw + 16 * i, ld_nc16(gd + i));   // static
   for (int i = lane; i < L.walk_stride / 4; i += nthr) sts128(s.walk + 16 * i, gw[i]);
+  if (L.off_durw >= 0) {
+    const uint4* gd = reinterpret_cast<const uint4*>(st.durw + (size_t)b * L.node_stride);
+    for (int i = lane; i < L.node_stride / 8; i += nthr) sts128(s.durw + 16 * i, ld_nc16(gd + i));   // static
+  }
   fill_pending(L, s, lane, fill_q, nthr);
 }
 
@@ -234,10 +236,11 @@ __device__ __forceinline__ int evaluate_instance(const Layout& L, const Inst& s,
 // Data-parallel pass over the walk words after an evaluation: for every operation record
 //   crit[v] = its critical predecessor = the FIRST predecessor in networkx's G.pred[v] insertion order that
 //             attains est[v] (job predecessor listed first iff the jobfirst bit is set or jp < mp; S, = 0, only
-//             if there is no other predecessor) -- this is what nx.dag_longest_path keeps per node;
-//   msu[v]  = its machine successor (0 = none), if want_msu.
-template <bool want_msu>
-__device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, int lane, int nthr = 32) {
+//             if there is no other predecessor) -- this is what nx.dag_longest_path keeps per node.
+// kMsu: also scatter every node's machine successor into the node-indexed uint16 array at `msu` (which lives in
+// the backward half of tq, so the pass must run after the latest start times have been consumed).
+template <bool kMsu>
+__device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, uint32_t msu, int lane, int nthr = 32) {
   for (int i = lane; i < L.n; i += nthr) {
     const unsigned w = (unsigned)lds32(s.walk + 4u * i);
     const unsigned wp = i > 0 ? (unsigned)lds32(s.walk + 4u * (i - 1)) : kWRowEnd;
@@ -248,12 +251,19 @@ __device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, int la
     const int fm = mp ? lds32(s.tq + 4u * mp) : -1;
     const bool take_jp = (fj >= 0) & ((fm < 0) | (fj > fm) | ((fj == fm) & (((w & kWJf) != 0u) | (jp < mp))));
     sts16(s.crit + 2u * v, (int)(take_jp ? jp : mp));
-    if (want_msu) {
+    if (kMsu) {   // msu[v] = machine successor (0 = none), node-indexed, for the ascending-source edge list
       const unsigned ms = (w & kWRowEnd) ? 0u : ((unsigned)lds32(s.walk + 4u * (i + 1)) & kWId);
-      sts16(s.msu + 2u * v, (int)ms);
+      sts16(msu + 2u * v, (int)ms);
     }
   }
-  __syncwarp();
+}
+
+// first operation of its job <=> (v-1) mod n_m == 0  (multiply-shift, exact for v < 2^16)
+__device__ __forceinline__ bool is_job_first(const Layout& L, int v) {
+  const unsigned x = (unsigned)(v - 1);
+  unsigned qd = __umulhi(x, L.magic_nm);
+  qd -= (qd * (unsigned)L.n_m > x) ? 1u : 0u;
+  return x == qd * (unsigned)L.n_m;
 }
 
 // Swap the adjacent machine pair a0 -> a1 (JsspN5.change_nxgraph_topology, env/environment.py:318-354) in the
@@ -313,7 +323,7 @@ __device__ __forceinline__ int n5_moves(const Layout& L, const Inst& s, uint32_t
   auto pf = [&](int i) -> int { return lds16(rp + 2u * (len - 1 - i)); };
   auto same = [&](int i) -> bool {   // ops i and i+1 of the path share a machine (0 <= i < rg)
     const int u = pf(i), w = pf(i + 1);
-    return !(u == w - 1 && !(lds16(s.durw + 2u * w) & kFirstFlag));
+    return !(u == w - 1 && !is_job_first(L, w));
   };
   for (int i0 = 0; i0 < rg; i0 += 32) {
     const int i = i0 + lane;

@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     }
     return;
   }
-  if (a.emc) link_pass<true>(L, s, lane); else link_pass<false>(L, s, lane);
+  const uint16_t* gdurw = a.st.durw + (size_t)b * L.node_stride;   // static node words (large instances)
+  const bool sm_dur = L.off_durw >= 0;
   const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   // latest start of S = min over job-first ops (:195 on the S row)
   int qs = 0;
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
       // common case: one FMA residual correction reproduces the IEEE quotient (verified on the host)
       const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
       for (int i = lane; i < n1; i += 32, xo += 96) {
-        const int d = lds16(s.durw + 2u * i) & kDurMask;
+        const int d = (sm_dur ? lds16(s.durw + 2u * i) : (int)__ldg(gdurw + i)) & kDurMask;
         const float fd = (float)d, fe = (float)(lds32(fin + 4u * i) - d), fl = fms - (float)lds32(q + 4u * i);
         float q0 = __fmul_rn(fd, rh), q1 = __fmul_rn(fe, rf), q2 = __fmul_rn(fl, rf);
         xo[0] = __fmaf_rn(__fmaf_rn(-ch, q0, fd), rh, q0);
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
       }
     } else {
       for (int i = lane; i < n1; i += 32, xo += 96) {
-        const int d = lds16(s.durw + 2u * i) & kDurMask;
+        const int d = (sm_dur ? lds16(s.durw + 2u * i) : (int)__ldg(gdurw + i)) & kDurMask;
         const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
         xo[0] = div_rn((float)d, a.high, a.r_high, a.div_high);
         xo[1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
@@ -406,14 +407,19 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   }
   if (a.ex_est) {
     for (int i = lane; i < n1; i += 32) {
-      const int d = lds16(s.durw + 2u * i) & kDurMask;
+      const int d = __ldg(gdurw + i) & kDurMask;
       a.ex_est[(size_t)b * n1 + i] = lds32(fin + 4u * i) - d;
       a.ex_lst[(size_t)b * n1 + i] = ms - lds32(q + 4u * i);
     }
   }
 
-  // 4. machine edges ascending by source (dag2pyg :300-305); successors were recorded by link_pass.
+  // 4. machine edges ascending by source (dag2pyg :300-305).  q is dead now: its storage holds the node-indexed
+  //    machine successors (msu) and, after them, the reversed critical path.
   //    Node ids of a slice fit 32 bits (checked in l2s_create): 32-bit arithmetic, 64-bit stores.
+  __syncwarp();
+  const uint32_t msu = q, rp = q + 2u * (uint32_t)n1;
+  if (a.emc) link_pass<true>(L, s, msu, lane); else link_pass<false>(L, s, msu, lane);
+  __syncwarp();
   if (a.emc) {
     const unsigned off = (unsigned)b * (unsigned)n1;
     uint2* src = reinterpret_cast<uint2*>(a.emc) + (size_t)b * L.e_mc;
@@ -421,7 +427,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     const unsigned below = (1u << lane) - 1u;
     for (int v0 = 1; v0 <= n; v0 += 32) {
       const int v = v0 + lane;
-      const unsigned sc = v <= n ? (unsigned)lds16(s.msu + 2u * v) : 0u;
+      const unsigned sc = v <= n ? (unsigned)lds16(msu + 2u * v) : 0u;
       const unsigned bal = __ballot_sync(kFull, sc != 0u);
       if (sc) {
         const int pos = __popc(bal & below);
@@ -435,8 +441,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   }
   __syncwarp();
 
-  // 5. critical path (nx.dag_longest_path, :77) and N5 move set (_get_pairs :84-105); q is dead: reuse it
-  const uint32_t rp = q;   // uint16 [n] reversed critical path
+  // 5. critical path (nx.dag_longest_path, :77) and N5 move set (_get_pairs :84-105)
   const int len = trace_path(L, s, ms, lane, rp);
   if (a.ex_path) {
     for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = lds16(rp + 2u * (len - 1 - i));
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     }
     return;
   }
-  if (a.emc) link_pass<true>(L, s, tid, nthr); else link_pass<false>(L, s, tid, nthr);
+  const uint16_t* gdurw = a.st.durw + (size_t)b * L.node_stride;
   const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   {
     int qs = 0;
@@ -586,7 +591,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     float* xo = a.x + (size_t)b * n1 * 3;
     const float fms = (float)ms;
     for (int i = tid; i < n1; i += nthr) {
-      const int d = lds16(s.durw + 2u * i) & kDurMask;
+      const int d = __ldg(gdurw + i) & kDurMask;
       const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
       xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
       xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
@@ -595,11 +600,15 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   }
   if (a.ex_est) {
     for (int i = tid; i < n1; i += nthr) {
-      const int d = lds16(s.durw + 2u * i) & kDurMask;
+      const int d = __ldg(gdurw + i) & kDurMask;
       a.ex_est[(size_t)b * n1 + i] = lds32(fin + 4u * i) - d;
       a.ex_lst[(size_t)b * n1 + i] = ms - lds32(q + 4u * i);
     }
   }
+  __syncthreads();   // q is dead from here on: its storage holds msu and then the reversed critical path
+  const uint32_t msu = q, rp = q + 2u * (uint32_t)n1;
+  if (a.emc) link_pass<true>(L, s, msu, tid, nthr); else link_pass<false>(L, s, msu, tid, nthr);
+  __syncthreads();
   if (a.emc) {
     // ordered compaction over contiguous node chunks, one per warp: count, exchange, write
     const int chunk = ((n + nw - 1) / nw + 31) & ~31;
@@ -607,7 +616,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     int cnt = 0;
     for (int v0 = vlo; v0 <= vhi; v0 += 32) {
       const int v = v0 + lane;
-      cnt += __popc(__ballot_sync(kFull, v <= vhi && lds16(s.msu + 2u * v) != 0));
+      cnt += __popc(__ballot_sync(kFull, v <= vhi && lds16(msu + 2u * v) != 0));
     }
     if (lane == 0) wcount[w] = cnt;
     __syncthreads();
@@ -619,7 +628,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     const unsigned below = (1u << lane) - 1u;
     for (int v0 = vlo; v0 <= vhi; v0 += 32) {
       const int v = v0 + lane;
-      const unsigned sc = v <= vhi ? (unsigned)lds16(s.msu + 2u * v) : 0u;
+      const unsigned sc = v <= vhi ? (unsigned)lds16(msu + 2u * v) : 0u;
       const unsigned bal = __ballot_sync(kFull, sc != 0u);
       if (sc) {
         const int pos = __popc(bal & below);
@@ -631,9 +640,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
       dst += adv;
     }
   }
-  __syncthreads();   // q is dead from here on: its storage becomes the reversed critical path
   if (w != 0) return;
-  const uint32_t rp = q;
   const int len = trace_path(L, s, ms, lane, rp);
   if (a.ex_path) {
     for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = lds16(rp + 2u * (len - 1 - i));
@@ -726,7 +733,8 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   if (ms < 0) status = -5;
   int np = 0;
   auto enumerate = [&]() {
-    link_pass<false>(L, s, lane);
+    link_pass<false>(L, s, 0u, lane);
+    __syncwarp();
     const int len = trace_path(L, s, ms, lane, rp);
     int c = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
       if (idx < pmax) { sts16(plist + 4u * idx, u); sts16(plist + 4u * idx + 2u, v); }
@@ -907,7 +915,7 @@ __global__ void __launch_bounds__(512) coo_ingest_kernel(const __grid_constant__
 }
 
 struct CooEvalArgs {
-  Layout L;            // tq + walk + durw offsets are reused; aux is not needed
+  Layout L;            // tq + walk offsets are reused
   long long B;
   const void* duration;
   int dur_i64;
@@ -916,7 +924,7 @@ struct CooEvalArgs {
   float* lst;
   float* ms;
   int bytes;           // smem per graph
-  int off_succ, off_heads;
+  int off_durw, off_succ, off_heads;
   long long expect_conj;
 };
 
@@ -929,6 +937,7 @@ __global__ void __launch_bounds__(128, 10) coo_eval_kernel(const __grid_constant
   const uint32_t base = smem_addr(smem_coo) + (uint32_t)w * (uint32_t)a.bytes;
   const Inst s = inst_view(L, base);
   const uint32_t succ = base + a.off_succ, heads = base + a.off_heads;   // uint16 [node_stride], uint16 [32]
+  const uint32_t durw = base + a.off_durw;                               // uint16 [node_stride] node words
   const int n = L.n, n1 = L.n1, n_m = L.n_m, n_j = L.n_j;
   if (b == 0 && lane == 0 && *a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
 
@@ -946,7 +955,7 @@ __global__ void __launch_bounds__(128, 10) coo_eval_kernel(const __grid_constant
       int word = (int)d;
       if (i >= 1 && i <= n) word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
       else if (d != 0) bad = 1;
-      sts16(s.durw + 2u * i, word);
+      sts16(durw + 2u * i, word);
       pos += step;
       if (pos >= n_m) pos -= n_m;
     }
@@ -987,7 +996,7 @@ __global__ void __launch_bounds__(128, 10) coo_eval_kernel(const __grid_constant
     for (int k = 0; k < n_j; ++k) {
       if (v == 0) { chain_ok = 0; break; }
       const int nx = lds16(succ + 2u * v);
-      sts32(s.walk + 4u * (lane * n_j + k), (int)make_walk(v, lds16(s.durw + 2u * v), false, k == n_j - 1));
+      sts32(s.walk + 4u * (lane * n_j + k), (int)make_walk(v, lds16(durw + 2u * v), false, k == n_j - 1));
       v = nx;
     }
     if (v != 0) chain_ok = 0;      // longer than n_j (or a cycle)
@@ -1014,7 +1023,7 @@ __global__ void __launch_bounds__(128, 10) coo_eval_kernel(const __grid_constant
   float* eo = a.est + b * n1;
   float* lo = a.lst + b * n1;
   for (int i = lane; i < n1; i += 32) {
-    const int d = lds16(s.durw + 2u * i) & kDurMask;
+    const int d = lds16(durw + 2u * i) & kDurMask;
     eo[i] = (float)(lds32(fin + 4u * i) - d);
     lo[i] = (float)(ms - lds32(q + 4u * i));
   }
