@@ -159,3 +159,32 @@ def test_c_oracle_greedy_reproduces_reference_stored_results(ds):
     _, logs = env.run("greedy", 500, log_steps=[int(s) for s in g["log_steps"]])
     assert np.array_equal(logs, g["incumbents"])
     assert np.array_equal(logs[list(g["log_steps"]).index(500)], g["stored_rows"][0])
+
+
+@pytest.mark.parametrize("n_j,n_m", [(2, 2), (3, 1), (2, 5), (5, 2), (3, 7), (4, 32), (13, 4), (33, 3)])
+def test_c_and_numpy_oracles_agree_on_odd_shapes(n_j, n_m):
+    """Edge shapes (single machine, two jobs, 32 machines, more jobs than a warp): both restatements must agree,
+    including the reference's IndexError corner (2-op critical path on one machine)."""
+    from oracle import c_oracle as CO
+    rng = np.random.RandomState(n_j * 37 + n_m)
+    B, K = 6, 25
+    dur = rng.randint(1, 6, size=(B, n_j, n_m))
+    mch = rng.random_sample((B, n_j, n_m)).argsort(axis=2) + 1
+    inst = np.stack([dur, mch], axis=1).astype(np.int32)
+    mseq = np.stack([O.rules_solver(i[0], i[1])[0] for i in inst])
+    for b in range(B):
+        assert np.array_equal(CO.rules_solver(inst[b, 0], inst[b, 1])[0], mseq[b])
+    env = O.OracleEnv(n_j, n_m, 1, 99)
+    try:
+        _, fa, _ = env.reset(inst, mseq=mseq)
+        taken, _ = O.run_policy(env, fa, "random", K, seed=5)
+        err = None
+    except IndexError:
+        err = -9
+    cenv = CO.CEnv(inst, mseq)
+    ctaken, _ = cenv.run("random", K, seed=5)
+    if err is None and cenv.status == 0:
+        assert np.array_equal(taken, ctaken)
+        assert np.array_equal(np.array([i.makespan for i in env.insts], dtype=np.float32), cenv.makespan)
+    else:
+        assert cenv.status == -9 or err == -9      # the IndexError corner must be flagged by at least the C oracle

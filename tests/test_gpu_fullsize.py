@@ -150,3 +150,35 @@ def test_evaluator_coo_full_size(n_j, n_m, B):
     mc[:, 0] = torch.flip(mc[:, 0], dims=[0])           # reverse one machine arc -> 2-cycle or broken chain
     with pytest.raises(L2SError):
         Evaluator().forward(torch.cat([state[1], mc], dim=1), dur.reshape(-1, 1), n_j, n_m)
+
+
+@pytest.mark.parametrize("n_j,n_m", [(2, 2), (3, 1), (2, 5), (5, 2), (3, 7), (4, 32), (13, 4), (33, 3), (40, 16), (40, 17)])
+def test_odd_shapes_against_c_oracle(n_j, n_m):
+    """Edge shapes: single machine, two jobs, 32 machines (all lanes), more jobs than lanes, the dual/single
+    sweep boundary (16 vs 17 machines).  Tie-heavy durations.  The 2-op-path IndexError corner is mirrored."""
+    from l2s_b200 import JsspN5
+    from oracle import c_oracle as CO
+    rng = np.random.RandomState(n_j * 37 + n_m)
+    B, K = 40, 25
+    dur = rng.randint(1, 6, size=(B, n_j, n_m))
+    mch = rng.random_sample((B, n_j, n_m)).argsort(axis=2) + 1
+    inst = np.stack([dur, mch], axis=1).astype(np.int32)
+    env = JsspN5(n_j, n_m, 1, 99)
+    mseq = np.stack([CO.rules_solver(i[0], i[1])[0] for i in inst])
+    cenv = CO.CEnv(inst, mseq)
+    ctaken, _ = cenv.run("random", K, seed=5)
+    if cenv.status == -9:
+        with pytest.raises(IndexError):
+            env.reset(inst, "fdd-divide-mwkr", "cuda")
+            env.run("random", K, seed=5)
+        return
+    assert cenv.status == 0
+    env.reset(inst, "fdd-divide-mwkr", "cuda")
+    assert np.array_equal(env.solutions().cpu().numpy(), mseq)
+    _, taken = env.run("random", K, seed=5, return_actions=True)
+    assert np.array_equal(taken.cpu().numpy(), ctaken)
+    state, fa, done = env.observe()
+    cenv.run("replay", 1, tape=np.zeros((B, 1, 2), np.int32), write_state=True)   # dummy step: refresh outputs
+    ex = env.export_state()
+    assert np.array_equal(ex["est"].cpu().numpy(), cenv.est) and np.array_equal(ex["lst"].cpu().numpy(), cenv.lst)
+    assert np.array_equal(np.array([0 if f == [[0, 0]] else len(f) for f in fa]), cenv.npairs)
