@@ -159,7 +159,8 @@ int64_t l2s_eval_coo_workspace_bytes(int n_j, int n_m, int64_t batch);
 /* edge_index [2,E] int64 COO in any order (conjunctive + machine arcs of `batch` complete selections),
  * duration [batch*(n+2)] int32 or int64 (`duration_is_i64`), outputs est/lst [batch*(n+2)] and
  * makespan [batch] as float32 (integer valued, like the reference).  status_flag: one int32 on the
- * device, set to a negative l2s_status if the input is not a batch of acyclic JSSP selections. */
+ * device that the CALLER zeroes; it is set (and then left) to a negative l2s_status if an input is not a batch
+ * of acyclic complete JSSP selections -- check it after every call or once after many. */
 int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duration, int duration_is_i64,
                  int n_j, int n_m, int64_t batch, float* est, float* lst, float* makespan,
                  void* workspace, int64_t workspace_bytes, int32_t* status_flag, int device, void* stream);

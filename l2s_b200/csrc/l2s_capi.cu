@@ -535,7 +535,6 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
     attr_set[device] = true;
   }
   CU(cudaMemsetAsync(workspace, 0, links + 16, s));
-  CU(cudaMemsetAsync(status_flag, 0, 4, s));
   CooIngestArgs g;
   memset(&g, 0, sizeof(g));
   g.ei = (const long long*)edge_index;

@@ -853,24 +853,32 @@ __device__ __forceinline__ unsigned fast_div(unsigned x, unsigned magic, unsigne
   return qd - ((qd * d > x) ? 1u : 0u);
 }
 
-// classify one edge (u -> v): returns 1 for a conjunctive arc, 0 after scattering a machine arc, -1 if malformed
+// classify one edge (u -> v): returns 1 for a conjunctive arc, 0 after scattering a machine arc, -1 if malformed.
+// Kept short on purpose (the ingest kernel is instruction-bound otherwise): one multiply-shift division to find
+// the graph, a second one only for edges that look like job arcs (v == u+1) or touch S / T.
 __device__ __forceinline__ int coo_edge(const CooIngestArgs& a, long long u, long long v) {
-  const int n = a.n, n1 = a.n1, n_m = a.n_m;
-  if (u < 0 || v < 0 || u >= a.B * n1 || v >= a.B * n1) return -1;
-  const unsigned bu = fast_div((unsigned)u, a.magic_n1, (unsigned)n1), bv = fast_div((unsigned)v, a.magic_n1, (unsigned)n1);
-  if (bu != bv) return -1;
-  const int ul = (int)((unsigned)u - bu * (unsigned)n1), vl = (int)((unsigned)v - bv * (unsigned)n1);
-  // position of u inside its job: (ul-1) % n_m ; last of its job <=> position == n_m-1
-  const unsigned ju = fast_div((unsigned)(ul > 0 ? ul - 1 : 0), a.magic_nm, (unsigned)n_m);
-  const int pos_u = ul - 1 - (int)(ju * (unsigned)n_m);
-  if (ul == 0) {                       // S -> first operation of a job
-    const unsigned jv = fast_div((unsigned)(vl > 0 ? vl - 1 : 0), a.magic_nm, (unsigned)n_m);
-    return (vl >= 1 && vl <= n && vl - 1 - (int)(jv * (unsigned)n_m) == 0) ? 1 : -1;
+  const unsigned n = (unsigned)a.n, n1 = (unsigned)a.n1, n_m = (unsigned)a.n_m;
+  const unsigned long long lim = (unsigned long long)a.B * n1;
+  if ((unsigned long long)u >= lim || (unsigned long long)v >= lim) return -1;   // also catches negatives
+  const unsigned bu = fast_div((unsigned)u, a.magic_n1, n1);
+  const unsigned base = bu * n1;
+  const unsigned ul = (unsigned)u - base, vl = (unsigned)v - base;     // vl wraps around if v is in an earlier graph
+  if (vl >= n1) return -1;                                             // different graph
+  if (ul - 1u < n && vl - 1u < n && vl != ul + 1u) {                   // op -> op, not consecutive: machine arc
+    a.ws.msucc[(size_t)bu * a.node_stride + ul] = (uint16_t)vl;
+    return 0;
   }
-  if (vl == n + 1) return (ul <= n && pos_u == n_m - 1) ? 1 : -1;   // last operation of a job -> T
-  if (ul > n || vl == 0) return -1;                                  // edge out of T or into S
-  if (vl == ul + 1 && pos_u != n_m - 1) return 1;                    // job arc
-  a.ws.msucc[(size_t)bu * a.node_stride + ul] = (uint16_t)vl;        // machine arc
+  if (ul == 0u) {                                                      // S -> first operation of a job
+    if (vl - 1u >= n) return -1;
+    const unsigned x = vl - 1u;
+    return x == fast_div(x, a.magic_nm, n_m) * n_m ? 1 : -1;
+  }
+  if (ul > n || vl == 0u) return -1;                                   // out of T / into S
+  // here vl == ul+1 (job arc unless u is the last of its job, then u+1 starts another job: machine arc), or v == T
+  const unsigned pos_u = (ul - 1u) - fast_div(ul - 1u, a.magic_nm, n_m) * n_m;
+  if (vl == n + 1u) return pos_u == n_m - 1u ? 1 : -1;                 // last operation of a job -> T
+  if (pos_u != n_m - 1u) return 1;                                     // job arc
+  a.ws.msucc[(size_t)bu * a.node_stride + ul] = (uint16_t)vl;          // machine arc between consecutive node ids
   return 0;
 }
 

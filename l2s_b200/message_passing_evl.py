@@ -53,6 +53,8 @@ class Evaluator:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
             self._flag = torch.zeros(1, dtype=torch.int32, device=device)
             self._sticky = torch.zeros(1, dtype=torch.int32, device=device)
+        if self.strict:
+            self._flag.zero_()
         est = torch.empty((N, 1), dtype=torch.float32, device=device)
         lst = torch.empty((N, 1), dtype=torch.float32, device=device)
         ms = torch.empty((B, 1), dtype=torch.float32, device=device)
@@ -60,12 +62,11 @@ class Evaluator:
         _capi.check(self._lib.l2s_eval_coo(
             C.c_void_p(ei.data_ptr()), ei.shape[1], C.c_void_p(dur.data_ptr()), 1 if dur.dtype == torch.int64 else 0,
             n_j, n_m, B, C.c_void_p(est.data_ptr()), C.c_void_p(lst.data_ptr()), C.c_void_p(ms.data_ptr()),
-            C.c_void_p(self._ws.data_ptr()), self._ws.numel(), C.c_void_p(self._flag.data_ptr()),
+            C.c_void_p(self._ws.data_ptr()), self._ws.numel(),
+            C.c_void_p((self._flag if self.strict else self._sticky).data_ptr()),
             device.index if device.index is not None else torch.cuda.current_device(), stream), "l2s_eval_coo")
         if self.strict:
             flag = int(self._flag.item())   # the reference synchronises 2*depth times per call; we do it once
             if flag < 0:
                 raise L2SError(flag, "Evaluator.forward")
-        else:
-            torch.minimum(self._sticky, self._flag, out=self._sticky)   # keep the most recent error for check()
         return est, lst, ms
