@@ -936,7 +936,7 @@ struct CooEvalArgs {
   long long expect_conj;
 };
 
-__global__ void __launch_bounds__(128, 10) coo_eval_kernel(const __grid_constant__ CooEvalArgs a) {
+__global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant__ CooEvalArgs a) {
   extern __shared__ __align__(16) unsigned char smem_coo[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + w;
