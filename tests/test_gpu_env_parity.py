@@ -163,3 +163,39 @@ def test_dummy_actions_freeze_state():
     s1, r, fa1, _ = env.step([[0, 0]] * inst.shape[0], "cuda")
     assert torch.equal(s0[0], s1[0]) and torch.equal(s0[2], s1[2]) and fa0 == fa1
     assert float(r.abs().sum()) == 0 and env.itr == 1
+
+
+def test_plist_initial_solutions_and_nonstrict_evaluator():
+    """'plist' initial solutions (env/environment.py:140-177,391-393): one shared random priority list; every
+    machine processes its operations in list order.  Checked through the evaluator against the numpy oracle."""
+    from l2s_b200 import Evaluator, JsspN5, L2SError
+    from oracle import l2s_oracle as O
+    g = np.load(os.path.join(GOLDEN, "traj_10x10.npz"))
+    inst = g["instances"]
+    np.random.seed(3)
+    env = JsspN5(10, 10, 1, 99)
+    state, fa, done = env.reset(inst, "plist", "cuda")
+    sol = env.solutions().cpu().numpy()
+    oenv = O.OracleEnv(10, 10, 1, 99)
+    ostate, ofa, odone = oenv.reset(inst, mseq=sol)
+    assert np.array_equal(state[0].cpu().numpy(), ostate[0]) and np.array_equal(state[2].cpu().numpy(), ostate[2])
+    assert [[list(map(int, p)) for p in f] for f in fa] == [[list(map(int, p)) for p in f] for f in ofa]
+    # every machine row holds exactly that machine's operations
+    mch = inst[:, 1].reshape(len(inst), -1)
+    for b in range(len(inst)):
+        for m in range(10):
+            assert (mch[b][sol[b, m] - 1] == m + 1).all()
+    # asynchronous evaluator: errors surface at check()
+    ev = Evaluator(strict=False)
+    ei = torch.cat([state[1], state[2]], dim=1)
+    dur = torch.from_numpy(np.concatenate([O.padded_durations(i[0]) for i in inst]).reshape(-1, 1)).cuda()
+    est, lst, ms = ev.forward(ei, dur, 10, 10)
+    ev.check()
+    assert torch.equal(ms, env.current_objs)
+    bad = ei.clone()
+    bad[:, -1] = bad[:, -2]
+    ev.forward(bad, dur, 10, 10)
+    with pytest.raises(L2SError):
+        ev.check()
+    ev.forward(ei, dur, 10, 10)
+    ev.check()          # the status word was cleared by the failed check
