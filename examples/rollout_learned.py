@@ -6,6 +6,7 @@
 with the shipped GIN+DGHAN weights.  Two modes:
   --mode lists   : the reference's own API (python lists between env and policy, one host round trip per step)
   --mode device  : move sets and actions stay on the GPU (`step_device` + `Actor.forward_device`), no host sync.
+  --mode graph   : device mode with the policy+step pair captured in one CUDA graph (`GraphedRollout`).
 
     python examples/rollout_learned.py --data tests/golden/policy/syn10x10.npy \
         --optimum tests/golden/policy/syn10x10_result.npy --weights tests/golden/policy/incumbent_10x10_gin+dghan.pth --steps 500
@@ -32,7 +33,13 @@ def rollout(instances, weights, steps, mode="device", seed=1, device="cuda", log
         policy.load_state_dict(torch.load(weights, map_location=device))
     results, t0 = {}, time.time()
     with torch.no_grad():      # the env is not differentiated through; the reference only keeps log_prob for training
-        if mode == "device":
+        if mode == "graph":
+            from l2s_b200.rollout import GraphedRollout
+            ro = GraphedRollout(env, policy).reset(instances, 'fdd-divide-mwkr', device)
+            logs = ro.run(steps, log_steps=log_steps)
+            for k, v in logs.items():
+                results[k] = v.cpu().numpy()
+        elif mode == "device":
             state, pairs, npairs, done = env.reset_device(instances, 'fdd-divide-mwkr', device)
             while env.itr < steps:
                 actions, _ = policy.forward_device(*state, pairs, npairs)
@@ -60,7 +67,7 @@ def main():
     ap.add_argument("--optimum", default="tests/golden/policy/syn10x10_result.npy")
     ap.add_argument("--weights", default="tests/golden/policy/incumbent_10x10_gin+dghan.pth")
     ap.add_argument("--steps", type=int, default=500)
-    ap.add_argument("--mode", default="device", choices=["device", "lists"])
+    ap.add_argument("--mode", default="device", choices=["device", "lists", "graph"])
     args = ap.parse_args()
     inst = np.load(args.data)
     res, secs = rollout(inst, args.weights, args.steps, args.mode)

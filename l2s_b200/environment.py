@@ -240,34 +240,42 @@ class JsspN5:
         state, _, pairs, npairs, done = self._launch_device(None, is_reset=True)
         return state, pairs, npairs, done
 
-    def step_device(self, actions):
+    def step_device(self, actions, out=None):
         """actions: int32 device tensor [B,2] ((0,0) = dummy).  One kernel launch, nothing is copied to the
         host and nothing synchronises; call `check_errors()` whenever convenient (e.g. every few hundred steps).
         Returns (state, reward [B,1], pairs int32 [B,pmax,2], npairs int32 [B], done bool [B,1])."""
         if self.reward_type not in _capi.REWARD:
             raise ValueError('reward type must be "yaoxin" or "consecutive".')
         assert actions.dtype == torch.int32 and actions.is_cuda and actions.shape == (self._key[0], 2)
-        out = self._launch_device(actions.contiguous(), is_reset=False)
+        res = self._launch_device(actions.contiguous(), is_reset=False, out=out)
         self.itr = self.itr + 1
-        return out
+        return res
 
     def check_errors(self):
         """Synchronise and raise if any instance reported a device-side error since the last check."""
         self._poll("step_device")
 
-    def _launch_device(self, actions, is_reset):
+    def device_buffers(self):
+        """Freshly allocated output tensors of one step (pass them as `out=` to `step_device` to write in place,
+        e.g. when the policy + step pair is captured in a CUDA graph)."""
         B, device = self._key[0], self._device
         n1 = self.n_oprs + 2
         e_mc = self.n_mch * (self.n_job - 1)
         pm = self._h_pairs.shape[1]
-        x = torch.empty((B * n1, 3), dtype=torch.float32, device=device)
-        emc = torch.empty((2, B * e_mc), dtype=torch.int64, device=device)
-        ms = torch.empty((B, 1), dtype=torch.float32, device=device)
-        inc = torch.empty((B, 1), dtype=torch.float32, device=device)
-        reward = torch.empty((B, 1), dtype=torch.float32, device=device)
-        done = torch.empty((B, 1), dtype=torch.bool, device=device)
-        pairs = torch.empty((B, pm, 2), dtype=torch.int32, device=device)
-        npairs = torch.empty((B,), dtype=torch.int32, device=device)
+        return dict(x=torch.empty((B * n1, 3), dtype=torch.float32, device=device),
+                    emc=torch.empty((2, B * e_mc), dtype=torch.int64, device=device),
+                    ms=torch.empty((B, 1), dtype=torch.float32, device=device),
+                    inc=torch.empty((B, 1), dtype=torch.float32, device=device),
+                    reward=torch.empty((B, 1), dtype=torch.float32, device=device),
+                    done=torch.empty((B, 1), dtype=torch.bool, device=device),
+                    pairs=torch.empty((B, pm, 2), dtype=torch.int32, device=device),
+                    npairs=torch.empty((B,), dtype=torch.int32, device=device))
+
+    def _launch_device(self, actions, is_reset, out=None):
+        device = self._device
+        o = out if out is not None else self.device_buffers()
+        x, emc, ms, inc, reward, done, pairs, npairs = (o[k] for k in ("x", "emc", "ms", "inc", "reward", "done",
+                                                                       "pairs", "npairs"))
         io = StepIO(actions=actions.data_ptr() if actions is not None else None, high=float(self.high),
                     fea_norm_const=float(self.fea_norm_const), reward_type=_capi.REWARD.get(self.reward_type, 0),
                     is_reset=1 if is_reset else 0, x=x.data_ptr(), edge_index_mc=emc.data_ptr(), makespan=ms.data_ptr(),

@@ -93,3 +93,26 @@ def test_reinforce_loss_matches_reference_formula_and_training_runs():
     after = torch.cat([p.detach().reshape(-1) for p in policy.parameters()])
     assert n_upd == 3 and not torch.equal(before, after) and torch.isfinite(after).all()
     assert (inc <= cur + 1e-6).all()
+
+
+def test_cuda_graph_rollout_matches_eager_device_rollout():
+    """policy+step captured in a CUDA graph: with a greedy (argmax) policy the trajectory is deterministic and must
+    equal the eager device-tensor loop step for step."""
+    from l2s_b200 import JsspN5
+    from l2s_b200.policy import Actor
+    from l2s_b200.rollout import GraphedRollout
+    inst = np.load(os.path.join(POL, "syn10x10.npy"))[:32]
+    policy = Actor(3, 128, embedding_l=4, policy_l=4, embedding_type='gin+dghan', heads=1, dropout=0.0).cuda()
+    policy.load_state_dict(torch.load(os.path.join(POL, "incumbent_10x10_gin+dghan.pth"), map_location="cuda"))
+    env = JsspN5(10, 10, 1, 99)
+    with torch.no_grad():
+        state, pairs, npairs, done = env.reset_device(inst, "fdd-divide-mwkr", "cuda")
+        for _ in range(40):
+            a, _ = policy.forward_device(*state, pairs, npairs, greedy=True)
+            state, r, pairs, npairs, done = env.step_device(a)
+    eager_cur, eager_inc = env.current_objs.clone(), env.incumbent_objs.clone()
+    env2 = JsspN5(10, 10, 1, 99)
+    ro = GraphedRollout(env2, policy, greedy=True).reset(inst, "fdd-divide-mwkr", "cuda")
+    ro.run(40)
+    assert env2.itr == 40
+    assert torch.equal(env2.current_objs, eager_cur) and torch.equal(env2.incumbent_objs, eager_inc)
