@@ -190,7 +190,7 @@ class Actor(nn.Module):
         has = npairs > 0
         score = score.masked_fill(~valid, -float("inf"))
         score = torch.where(has.unsqueeze(1), score, torch.zeros_like(score))    # no move: uniform dummy row
-        dist = Categorical(logits=score)
+        dist = Categorical(logits=score, validate_args=False)   # no host-side validation: keeps the call capturable
         choice = score.argmax(dim=1) if greedy else dist.sample()
         log_prob = torch.where(has, dist.log_prob(choice), torch.zeros_like(choice, dtype=score.dtype)).unsqueeze(1)
         act = torch.gather(pairs, 1, choice.view(B, 1, 1).expand(B, 1, 2)).squeeze(1)

@@ -44,6 +44,7 @@ class GraphedRollout:
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self._one_step()
+        self.env.itr -= 1        # the captured call only recorded the work; it did not advance the search
         return self
 
     def run(self, until_itr, log_steps=()):
