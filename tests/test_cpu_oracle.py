@@ -188,3 +188,42 @@ def test_c_and_numpy_oracles_agree_on_odd_shapes(n_j, n_m):
         assert np.array_equal(np.array([i.makespan for i in env.insts], dtype=np.float32), cenv.makespan)
     else:
         assert cenv.status == -9 or err == -9      # the IndexError corner must be flagged by at least the C oracle
+
+
+def test_dropin_module_paths_resolve_to_the_cuda_implementation():
+    """`from env.environment import JsspN5, BatchGraph` (test_learned.py:6, n-step_reinforce.py:8) resolves to this
+    package once l2s_b200/dropin is on sys.path; signatures mirror the reference's."""
+    import importlib
+    import inspect
+    import sys
+    import l2s_b200
+    dropin = os.path.join(os.path.dirname(l2s_b200.__file__), "dropin")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "env" or k.startswith("env.")}
+    sys.path.insert(0, dropin)
+    try:
+        envmod = importlib.import_module("env.environment")
+        evl = importlib.import_module("env.message_passing_evl")
+        gen = importlib.import_module("env.generateJSP")
+        assert envmod.JsspN5 is l2s_b200.JsspN5 and envmod.BatchGraph is l2s_b200.BatchGraph
+        assert evl.Evaluator is l2s_b200.Evaluator
+        sig = inspect.signature(envmod.JsspN5.__init__)
+        assert list(sig.parameters)[1:8] == ["n_job", "n_mch", "low", "high", "reward_type", "fea_norm_const",
+                                              "evaluator_type"]
+        assert sig.parameters["reward_type"].default == "yaoxin" and sig.parameters["fea_norm_const"].default == 1000
+        assert list(inspect.signature(envmod.JsspN5.reset).parameters)[1:5] == ["instances", "init_type", "device", "plot"]
+        assert list(inspect.signature(envmod.JsspN5.step).parameters)[1:4] == ["actions", "device", "plot"]
+        assert list(inspect.signature(evl.Evaluator.forward).parameters)[1:] == ["edge_index", "duration", "n_j", "n_m"]
+        np.random.seed(0)
+        t, m = gen.uni_instance_gen(7, 5, 1, 99)
+        assert t.shape == (7, 5) and t.min() >= 1 and t.max() <= 98
+        assert (np.sort(m, axis=1) == np.arange(1, 6)).all()
+        bg = envmod.BatchGraph()
+        bg.wrapper(1, 2, 3, 4)
+        assert (bg.x, bg.edge_index_pc, bg.edge_index_mc, bg.batch) == (1, 2, 3, 4)
+        bg.clean()
+        assert bg.x is None
+    finally:
+        sys.path.remove(dropin)
+        for k in [k for k in sys.modules if k == "env" or k.startswith("env.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
