@@ -182,3 +182,48 @@ def test_odd_shapes_against_c_oracle(n_j, n_m):
     ex = env.export_state()
     assert np.array_equal(ex["est"].cpu().numpy(), cenv.est) and np.array_equal(ex["lst"].cpu().numpy(), cenv.lst)
     assert np.array_equal(np.array([0 if f == [[0, 0]] else len(f) for f in fa]), cenv.npairs)
+
+
+def test_randomised_shapes_and_durations_against_c_oracle():
+    """Fuzz: 24 random (n_j, n_m, duration range, init rule) combinations, each stepped through the per-step API with
+    every output compared to the plain-C oracle at every step (bit-exact x, edges, pairs, rewards, incumbents)."""
+    from l2s_b200 import JsspN5
+    from oracle import c_oracle as CO
+    rng = np.random.RandomState(2024)
+    for case in range(24):
+        n_j, n_m = int(rng.randint(3, 28)), int(rng.randint(2, 24))
+        hi = int(rng.choice([3, 5, 20, 99, 400]))
+        B, K = int(rng.randint(3, 40)), int(rng.randint(5, 30))
+        rule = str(rng.choice(["fdd-divide-mwkr", "spt"]))
+        dur = rng.randint(1, hi + 1, size=(B, n_j, n_m))
+        mch = rng.random_sample((B, n_j, n_m)).argsort(axis=2) + 1
+        inst = np.stack([dur, mch], axis=1).astype(np.int32)
+        fea = float(rng.choice([1000, 999.5, 37]))
+        env = JsspN5(n_j, n_m, 1, max(hi, 99), fea_norm_const=fea, reward_type=str(rng.choice(["yaoxin", "consecutive"])))
+        try:
+            state, fa, done = env.reset(inst, rule, "cuda")
+        except IndexError:
+            continue          # the reference's 2-op-path corner; covered elsewhere
+        mseq = np.stack([CO.rules_solver(i[0], i[1], rule, max(hi, 99))[0] for i in inst])
+        assert np.array_equal(env.solutions().cpu().numpy(), mseq), "case %d initial solution" % case
+        cenv = CO.CEnv(inst, mseq, high=float(max(hi, 99)), fea=fea, pmax=env.pmax)
+        if cenv.status != 0:
+            continue
+        prev_cur = cenv.makespan.copy()
+        for k in range(K):
+            acts = [f[int(rng.randint(len(f)))] for f in fa]
+            prev_inc = cenv.incumbent.copy()
+            cenv.run("replay", 1, tape=np.array(acts, dtype=np.int32).reshape(B, 1, 2), write_state=True)
+            if cenv.status != 0:
+                break
+            state, reward, fa, done = env.step(acts, "cuda")
+            assert np.array_equal(state[0].cpu().numpy(), cenv.x), "case %d step %d x" % (case, k)
+            assert np.array_equal(state[2].cpu().numpy(), cenv.emc), "case %d step %d edges" % (case, k)
+            assert np.array_equal(env.current_objs.cpu().numpy().reshape(-1), cenv.makespan)
+            assert np.array_equal(env.incumbent_objs.cpu().numpy().reshape(-1), cenv.incumbent)
+            want_r = (prev_cur - cenv.makespan) if env.reward_type == "consecutive" else np.maximum(prev_inc - cenv.makespan, 0)
+            assert np.array_equal(reward.cpu().numpy().reshape(-1), want_r.astype(np.float32))
+            prev_cur = cenv.makespan.copy()
+            for b in range(B):
+                want = cenv.pairs[b, :cenv.npairs[b]].tolist() if cenv.npairs[b] else [[0, 0]]
+                assert fa[b] == want, "case %d step %d instance %d pairs" % (case, k, b)
