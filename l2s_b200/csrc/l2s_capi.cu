@@ -182,7 +182,7 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   // few instances per SM (large graphs): give every instance a whole CTA so that the SM is not left idle
   {
     const long long per_sm = (long long)(kSmemPerSm / ((size_t)L.bytes + kSmemCtaReserve));
-    h->cta_warps = per_sm < 16 ? (per_sm <= 8 ? 8 : 4) : 0;   // measured: 100x20/150x25 best at 8, 50x20 at 4, 30x20 warp-per-instance
+    h->cta_warps = per_sm < 16 ? (per_sm <= 4 ? 8 : 4) : 0;   // measured: 150x25 best at 8, 100x20 / 50x20 at 4, 30x20 warp-per-instance
     if (const char* e = getenv("L2S_CTA_WARPS")) h->cta_warps = atoi(e);
     if (h->cta_warps > 8) h->cta_warps = 8;
   }

@@ -609,19 +609,23 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   const uint32_t msu = q, rp = q + 2u * (uint32_t)n1;
   if (a.emc) link_pass<true>(L, s, msu, tid, nthr); else link_pass<false>(L, s, msu, tid, nthr);
   __syncthreads();
-  if (a.emc) {
-    // ordered compaction over contiguous node chunks, one per warp: count, exchange, write
-    const int chunk = ((n + nw - 1) / nw + 31) & ~31;
-    const int vlo = 1 + w * chunk, vhi = min(n, vlo + chunk - 1);
+  // the edge list is written by warps 1.. while warp 0 already traces the critical path (a single-warp CTA does
+  // both in turn); msu and rp are disjoint parts of the dead q half
+  const int ew = nw > 1 ? nw - 1 : 1, myw = nw > 1 ? w - 1 : 0;
+  if (a.emc && (nw == 1 || w > 0)) {
+    // ordered compaction over contiguous node chunks, one per writer warp: count, exchange, write
+    const int chunk = ((n + ew - 1) / ew + 31) & ~31;
+    const int vlo = 1 + myw * chunk, vhi = min(n, vlo + chunk - 1);
     int cnt = 0;
     for (int v0 = vlo; v0 <= vhi; v0 += 32) {
       const int v = v0 + lane;
       cnt += __popc(__ballot_sync(kFull, v <= vhi && lds16(msu + 2u * v) != 0));
     }
-    if (lane == 0) wcount[w] = cnt;
-    __syncthreads();
+    if (lane == 0) wcount[myw] = cnt;
+    if (nw > 1) asm volatile("bar.sync 1, %0;" ::"r"(ew * 32));   // writer warps only (named barrier 1)
+    else __syncwarp();
     int base = 0;
-    for (int k = 0; k < w; ++k) base += wcount[k];
+    for (int k = 0; k < myw; ++k) base += wcount[k];
     const unsigned off = (unsigned)b * (unsigned)n1;
     uint2* src = reinterpret_cast<uint2*>(a.emc) + (size_t)b * L.e_mc + base;
     uint2* dst = src + (size_t)a.B * L.e_mc;
