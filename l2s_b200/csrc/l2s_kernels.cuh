@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     }
   }
 
-  // 2. evaluate (Evaluator.forward, env/message_passing_evl.py:161-199) + critical predecessors
+  // 2. evaluate (Evaluator.forward, env/message_passing_evl.py:161-199): forward + backward sweep
   const int ms = evaluate_instance(L, s, lane, true);
   if (ms < 0) {
     status = -5;
