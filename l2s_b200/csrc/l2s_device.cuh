@@ -129,16 +129,43 @@ __device__ __forceinline__ void fill_pending(const Layout& L, const Inst& s, int
   for (int i = lane; i < cnt; i += nthr) sts128(s.tq + 16 * i, pending);
 }
 
-// Coalesced 16-byte staging of one instance's state into shared memory + sentinel fill of tq.
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: one lane moves a whole array into shared memory
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// Staging of one instance's state into shared memory: ONE elected lane issues TMA bulk copies (walk words and,
+// for small instances, the static node words; 16-byte aligned, sizes multiples of 16) that complete on an
+// mbarrier in the instance's scratch words, while all lanes fill tq with the "pending" sentinel.  Every lane
+// then waits on the barrier (phase 0; each instance slot is used once per kernel).
 __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, const State& st, int b, int lane,
                                                bool fill_q, int nthr = 32) {
-  const uint4* gw = reinterpret_cast<const uint4*>(st.walk + (size_t)b * L.walk_stride);
-  for (int i = lane; i < L.walk_stride / 4; i += nthr) sts128(s.walk + 16 * i, gw[i]);
-  if (L.off_durw >= 0) {
-    const uint4* gd = reinterpret_cast<const uint4*>(st.durw + (size_t)b * L.node_stride);
-    for (int i = lane; i < L.node_stride / 8; i += nthr) sts128(s.durw + 16 * i, ld_nc16(gd + i));   // static
+  const uint32_t bar = s.misc + 8u;
+  if (lane == 0) {
+    const uint32_t wbytes = (uint32_t)L.walk_stride * 4u, dbytes = L.off_durw >= 0 ? (uint32_t)L.node_stride * 2u : 0u;
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, wbytes + dbytes);
+    bulk_g2s(s.walk, st.walk + (size_t)b * L.walk_stride, wbytes, bar);
+    if (dbytes) bulk_g2s(s.durw, st.durw + (size_t)b * L.node_stride, dbytes, bar);
   }
   fill_pending(L, s, lane, fill_q, nthr);
+  if (nthr > 32) __syncthreads(); else __syncwarp();   // the barrier word is initialised before anyone polls it
+  mbar_wait(bar, 0);
 }
 
 // ------------------------------------------------------------------------------------------------------
