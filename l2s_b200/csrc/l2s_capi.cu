@@ -209,6 +209,12 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   CU(cudaMalloc(&st.cur, B * 4));
   CU(cudaMalloc(&st.inc, B * 4));
   CU(cudaMalloc(&st.err, 4));
+  {
+    int32_t* page = nullptr;
+    CU(cudaMalloc(&page, (size_t)2 * L.n1p * 4));
+    CU(cudaMemset(page, 0xff, (size_t)2 * L.n1p * 4));
+    st.pending_page = page;
+  }
   CU(cudaMemset(st.durw, 0, B * L.node_stride * 2));
   CU(cudaMemset(st.mch, 0, B * L.mch_stride));
   CU(cudaMemset(st.walk, 0, B * L.walk_stride * 4));
@@ -246,6 +252,7 @@ int l2s_destroy(l2s_handle h) {
   cudaSetDevice(h->device);
   cudaFree(h->st.durw); cudaFree(h->st.mch); cudaFree(h->st.walk); cudaFree(h->st.where);
   cudaFree(h->st.tabu); cudaFree(h->st.cur); cudaFree(h->st.inc); cudaFree(h->st.err);
+  cudaFree((void*)h->st.pending_page);
   cudaFree(h->d_pack); cudaFreeHost(h->h_pack); cudaFree(h->d_actions); cudaFreeHost(h->h_actions);
   free(h);
   return L2S_OK;

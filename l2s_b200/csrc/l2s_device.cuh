@@ -72,6 +72,7 @@ struct State {
   int32_t* cur;     // [B] current makespan
   int32_t* inc;     // [B] incumbent makespan
   int32_t* err;     // [1] first device-side error: (code<<24)|instance  (0 = none)
+  const int32_t* pending_page;   // [2*n1p] words of -1: source of the TMA fill of tq
 };
 
 // 32-bit shared-memory addressing (keeps the hot loops free of 64-bit generic pointer arithmetic)
@@ -151,19 +152,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // Staging of one instance's state into shared memory: ONE elected lane issues TMA bulk copies (walk words and,
 // for small instances, the static node words; 16-byte aligned, sizes multiples of 16) that complete on an
-// mbarrier in the instance's scratch words, while all lanes fill tq with the "pending" sentinel.  Every lane
-// then waits on the barrier (phase 0; each instance slot is used once per kernel).
+// mbarrier in the instance's scratch words; the "pending" sentinels of tq are bulk-copied from a page of -1 words
+// (L2 resident).  Every lane then waits on the barrier (phase 0; each instance slot is used once per kernel).
 __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, const State& st, int b, int lane,
                                                bool fill_q, int nthr = 32) {
   const uint32_t bar = s.misc + 8u;
   if (lane == 0) {
     const uint32_t wbytes = (uint32_t)L.walk_stride * 4u, dbytes = L.off_durw >= 0 ? (uint32_t)L.node_stride * 2u : 0u;
+    // warp-per-instance: the "pending" sentinels come from a -1 page in L2 too; a whole CTA fills them itself
+    const uint32_t tbytes = nthr > 32 ? 0u : (fill_q ? 2u : 1u) * (uint32_t)L.n1p * 4u;
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, wbytes + dbytes);
+    mbar_expect_tx(bar, wbytes + dbytes + tbytes);
     bulk_g2s(s.walk, st.walk + (size_t)b * L.walk_stride, wbytes, bar);
     if (dbytes) bulk_g2s(s.durw, st.durw + (size_t)b * L.node_stride, dbytes, bar);
+    if (tbytes) bulk_g2s(s.tq, st.pending_page, tbytes, bar);
   }
-  fill_pending(L, s, lane, fill_q, nthr);
+  if (nthr > 32) fill_pending(L, s, lane, fill_q, nthr);
   if (nthr > 32) __syncthreads(); else __syncwarp();   // the barrier word is initialised before anyone polls it
   mbar_wait(bar, 0);
 }
