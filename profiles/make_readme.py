@@ -94,8 +94,9 @@ Reading: the kernel is **instruction-issue bound** (issue slots ~70 % busy, LSU 
 bound: the dependent integer chains of the longest-path sweep plus output formatting cost ~3.3 k warp
 instructions per instance-step. DRAM traffic per launch is BELOW the algorithmic 110 MB because ncu replays one
 launch with the 67 MB of x / edge_index_mc output still resident in the 126 MB L2 (write-back); there are no
-wasted re-reads (state is staged once into shared memory). 64 registers/32 resident warps per SM measured
-better than 48/40 and 40/48 (spills + rematerialisation cost more issue slots than the extra warps hide).
+wasted re-reads (state is staged once into shared memory by TMA bulk copies). Register caps of 64, 56 and 48 per
+thread (32-40 resident warps) measure the same within 1 %: the kernel is issue-bound, not occupancy-bound; a
+40-register cap spills and is slower.
 
 Per-phase shares (`by_phase.py` on the source-correlated export of the same capture):
 
