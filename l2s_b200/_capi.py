@@ -94,3 +94,30 @@ def check(status, where=""):
     if status < 0:
         raise L2SError(status, where)
     return status
+
+
+_pylists = None
+
+
+def pylists():
+    """Optional CPython glue (l2s_pylists.so): builds the nested move lists / parses action lists at C speed.
+    Returns None if it is not built; callers then use the (slower) numpy route.  Formatting only -- no compute."""
+    global _pylists
+    if _pylists is None:
+        path = _build.PYLISTS_PATH
+        if not os.path.isfile(path):
+            try:
+                _build.build_pylists()
+            except Exception:
+                _pylists = False
+                return None
+        try:
+            L = C.PyDLL(path)
+            L.l2s_build_move_lists.restype = C.py_object
+            L.l2s_build_move_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+            L.l2s_parse_actions.restype = C.c_int
+            L.l2s_parse_actions.argtypes = [C.py_object, C.c_void_p, C.c_int]
+            _pylists = L
+        except Exception:
+            _pylists = False
+    return _pylists or None

@@ -23,8 +23,30 @@ def _stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+PYLISTS_SRC = os.path.join(CSRC, "l2s_pylists.c")
+PYLISTS_PATH = os.path.join(LIB_DIR, "l2s_pylists.so")
+
+
+def build_pylists(force=False):
+    """CPython glue (list <-> pinned buffer conversions of the reference's list-shaped API); gcc, no CUDA."""
+    import sysconfig
+    if not force and os.path.isfile(PYLISTS_PATH) and os.path.getmtime(PYLISTS_PATH) >= os.path.getmtime(PYLISTS_SRC):
+        return PYLISTS_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", PYLISTS_PATH, PYLISTS_SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed:\n%s" % res.stderr)
+    return PYLISTS_PATH
+
+
 def build(force=False, verbose=False):
     """Compile the library if it is missing or older than its sources.  Returns the library path."""
+    try:
+        build_pylists(force)
+    except Exception as e:   # optional accelerator of the Python list conversions only
+        if verbose:
+            print("l2s_pylists not built:", e)
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")

@@ -188,8 +188,14 @@ class JsspN5:
         like env/environment.py:356-387."""
         if self.reward_type not in _capi.REWARD:
             raise ValueError('reward type must be "yaoxin" or "consecutive".')
-        acts = np.asarray(actions, dtype=np.int32).reshape(-1, 2)
-        assert acts.shape[0] == self._key[0], "one action per instance"
+        glue = _capi.pylists()
+        if glue is not None and not isinstance(actions, np.ndarray):
+            if glue.l2s_parse_actions(actions, self._h_actions.ctypes.data, self._key[0]) != 0:
+                raise RuntimeError("could not parse actions")      # (a Python exception is normally already set)
+            acts = self._h_actions
+        else:
+            acts = np.asarray(actions, dtype=np.int32).reshape(-1, 2)
+            assert acts.shape[0] == self._key[0], "one action per instance"
         out = self._launch(acts, self._device, is_reset=False)
         self.itr = self.itr + 1
         return out
@@ -352,7 +358,8 @@ class JsspN5:
                     reward=reward.data_ptr(), done=done.data_ptr(), pairs=None, npairs=None, status=None)
         a_ptr = None
         if acts is not None:
-            self._h_actions[:] = acts
+            if acts is not self._h_actions:
+                self._h_actions[:] = acts
             a_ptr = self._h_actions_ptr
         _capi.check(self._lib.l2s_step_host(self._h, C.byref(io), a_ptr, None, None, None, None, None, None,
                                             _stream_ptr(device)), "l2s_step")
@@ -365,13 +372,17 @@ class JsspN5:
         self.current_objs = ms
         self.incumbent_objs = inc
         npairs = self._h_npairs
-        mask = np.arange(self._h_pairs.shape[1])[None, :] < npairs[:, None]
-        flat = self._h_pairs[mask].tolist()
-        ends = np.cumsum(npairs).tolist()
-        fa, s = [], 0
-        for e in ends:
-            fa.append(flat[s:e] if e > s else [[0, 0]])
-            s = e
+        glue = _capi.pylists()
+        if glue is not None:
+            fa = glue.l2s_build_move_lists(self._h_pairs.ctypes.data, npairs.ctypes.data, B, self._h_pairs.shape[1])
+        else:
+            mask = np.arange(self._h_pairs.shape[1])[None, :] < npairs[:, None]
+            flat = self._h_pairs[mask].tolist()
+            ends = np.cumsum(npairs).tolist()
+            fa, s = [], 0
+            for e in ends:
+                fa.append(flat[s:e] if e > s else [[0, 0]])
+                s = e
         self._fa = fa
         self._flag = ~done
         return (x, self._const[0], emc, self._const[1]), reward, fa, done

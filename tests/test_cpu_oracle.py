@@ -227,3 +227,28 @@ def test_dropin_module_paths_resolve_to_the_cuda_implementation():
         for k in [k for k in sys.modules if k == "env" or k.startswith("env.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_python_list_glue_matches_numpy_route():
+    """l2s_pylists.so (CPython glue for the reference's list-shaped API) == the numpy conversions it replaces."""
+    from l2s_b200 import _capi
+    g = _capi.pylists()
+    assert g is not None, "l2s_pylists.so should build wherever Python.h and gcc are present"
+    rng = np.random.RandomState(0)
+    B, pm = 257, 12
+    npairs = rng.randint(0, pm + 1, size=B).astype(np.int32)
+    pairs = rng.randint(1, 4000, size=(B, pm, 2)).astype(np.uint16)
+    fa = g.l2s_build_move_lists(pairs.ctypes.data, npairs.ctypes.data, B, pm)
+    want = [pairs[b, :npairs[b]].tolist() if npairs[b] else [[0, 0]] for b in range(B)]
+    assert fa == want and all(type(p) is list and type(p[0]) is int for f in fa for p in f)
+    acts = [f[len(f) // 2] for f in fa]
+    out = np.zeros((B, 2), np.int32)
+    assert g.l2s_parse_actions(acts, out.ctypes.data, B) == 0 and np.array_equal(out, np.array(acts))
+    mixed = [(np.int64(a[0]), np.int32(a[1])) for a in acts]           # tuples of numpy integers are fine too
+    assert g.l2s_parse_actions(mixed, out.ctypes.data, B) == 0 and np.array_equal(out, np.array(acts))
+    with pytest.raises(AssertionError):
+        g.l2s_parse_actions(acts[:-1], out.ctypes.data, B)
+    with pytest.raises((ValueError, TypeError)):
+        g.l2s_parse_actions([[1, 2, 3]] * B, out.ctypes.data, B)
+    with pytest.raises(TypeError):
+        g.l2s_parse_actions([[1.5, 2]] * B, out.ctypes.data, B)
