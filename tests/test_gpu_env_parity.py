@@ -199,3 +199,29 @@ def test_plist_initial_solutions_and_nonstrict_evaluator():
         ev.check()
     ev.forward(ei, dur, 10, 10)
     ev.check()          # the status word was cleared by the failed check
+
+
+def test_device_api_errors_are_reported_asynchronously():
+    """step_device never synchronises; an illegal action surfaces at check_errors() / the next host-side step, and
+    a replayed tape with an illegal action raises from run()."""
+    import networkx as nx
+    from l2s_b200 import JsspN5
+    g = np.load(os.path.join(GOLDEN, "traj_10x5.npz"))
+    inst = g["instances"]
+    env = JsspN5(10, 5, 1, 99)
+    state, pairs, npairs, done = env.reset_device(inst, "fdd-divide-mwkr", "cuda", init_solutions=g["mseq0"])
+    acts = pairs[:, 0, :].clone()
+    acts[1] = torch.tensor([1, 2], dtype=torch.int32)          # same job: never an adjacent machine pair
+    before = env.solutions().clone()
+    env.step_device(acts)
+    with pytest.raises(nx.NetworkXError):
+        env.check_errors()
+    after = env.solutions()
+    assert torch.equal(before[1], after[1])                     # the offending instance was left untouched
+    env.check_errors()                                          # error word was drained
+    env2 = JsspN5(10, 5, 1, 99)
+    env2.reset(inst, "fdd-divide-mwkr", "cuda", init_solutions=g["mseq0"])
+    tape = g["tape"][:, :5].copy()
+    tape[3, 2] = [7, 7]
+    with pytest.raises(nx.NetworkXError):
+        env2.run("replay", 5, tape=tape)
