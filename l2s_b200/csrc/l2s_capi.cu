@@ -568,9 +568,12 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   g.magic_n1 = (unsigned)((1ull << 32) / (unsigned)(n + 2)) + 1u;
   g.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   g.ws = a.ws;
-  long long blocks = (n_edges + 8 * 512 - 1) / (8 * 512);   // ~8 edges per thread (two 2-edge vector trips x2)
+  g.lim = (unsigned)(batch * (n + 2));
+  g.vec_ok = (n_edges % 2 == 0) && (((unsigned long long)edge_index & 15ull) == 0);
+  const long long items = g.vec_ok ? n_edges / 2 : n_edges;           // loads per row
+  long long blocks = (items + 256 * kIngestTrips - 1) / (256 * kIngestTrips);
   if (blocks < 1) blocks = 1;
-  coo_ingest_kernel<<<(unsigned)blocks, 512, 0, s>>>(g);
+  coo_ingest_kernel<<<(unsigned)blocks, 256, 0, s>>>(g);
   CU(cudaGetLastError());
   coo_eval_kernel<<<(unsigned)((batch + W - 1) / W), W * 32, (size_t)W * a.bytes, s>>>(a);
   CU(cudaGetLastError());

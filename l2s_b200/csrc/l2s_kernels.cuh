@@ -845,7 +845,9 @@ struct CooIngestArgs {
   const long long* ei;
   long long E, B;
   int n_j, n_m, n, n1, node_stride;
-  unsigned magic_n1, magic_nm;   // ceil(2^32 / d): exact x / d for x < 2^31 / d ... see fast_div
+  unsigned magic_n1, magic_nm;   // floor(2^32 / d) + 1, see fast_div
+  unsigned lim;                  // batch * (n+2)
+  int vec_ok;                    // rows 16-byte aligned and E even: 2 edges per load
   CooWs ws;
 };
 
@@ -858,18 +860,20 @@ __device__ __forceinline__ unsigned fast_div(unsigned x, unsigned magic, unsigne
 }
 
 // classify one edge (u -> v): returns 1 for a conjunctive arc, 0 after scattering a machine arc, -1 if malformed.
-// Kept short on purpose (the ingest kernel is instruction-bound otherwise): one multiply-shift division to find
-// the graph, a second one only for edges that look like job arcs (v == u+1) or touch S / T.
-__device__ __forceinline__ int coo_edge(const CooIngestArgs& a, long long u, long long v) {
+// Kept short on purpose (the ingest kernel is instruction-bound otherwise): 32-bit arithmetic (the host guarantees
+// batch*(n+2) < 2^31), one multiply-shift division to find the graph, a second one only for edges that look like
+// job arcs (v == u+1) or touch S / T.
+__device__ __forceinline__ int coo_edge(const CooIngestArgs& a, long long u64, long long v64) {
   const unsigned n = (unsigned)a.n, n1 = (unsigned)a.n1, n_m = (unsigned)a.n_m;
-  const unsigned long long lim = (unsigned long long)a.B * n1;
-  if ((unsigned long long)u >= lim || (unsigned long long)v >= lim) return -1;   // also catches negatives
-  const unsigned bu = fast_div((unsigned)u, a.magic_n1, n1);
+  if ((unsigned long long)(u64 | v64) >> 31) return -1;                // negative or >= 2^31
+  const unsigned u = (unsigned)u64, v = (unsigned)v64;
+  if (u >= a.lim || v >= a.lim) return -1;
+  const unsigned bu = fast_div(u, a.magic_n1, n1);
   const unsigned base = bu * n1;
-  const unsigned ul = (unsigned)u - base, vl = (unsigned)v - base;     // vl wraps around if v is in an earlier graph
+  const unsigned ul = u - base, vl = v - base;                         // vl wraps around if v is in an earlier graph
   if (vl >= n1) return -1;                                             // different graph
   if (ul - 1u < n && vl - 1u < n && vl != ul + 1u) {                   // op -> op, not consecutive: machine arc
-    a.ws.msucc[(size_t)bu * a.node_stride + ul] = (uint16_t)vl;
+    a.ws.msucc[bu * (unsigned)a.node_stride + ul] = (uint16_t)vl;
     return 0;
   }
   if (ul == 0u) {                                                      // S -> first operation of a job
@@ -882,46 +886,57 @@ __device__ __forceinline__ int coo_edge(const CooIngestArgs& a, long long u, lon
   const unsigned pos_u = (ul - 1u) - fast_div(ul - 1u, a.magic_nm, n_m) * n_m;
   if (vl == n + 1u) return pos_u == n_m - 1u ? 1 : -1;                 // last operation of a job -> T
   if (pos_u != n_m - 1u) return 1;                                     // job arc
-  a.ws.msucc[(size_t)bu * a.node_stride + ul] = (uint16_t)vl;          // machine arc between consecutive node ids
+  a.ws.msucc[bu * (unsigned)a.node_stride + ul] = (uint16_t)vl;        // machine arc between consecutive node ids
   return 0;
 }
 
-// One thread takes 4 edges per trip as two 16-byte loads per row of the [2,E] list (8 loads in flight per
-// thread with the 2x unroll): the kernel is a pure HBM stream (16 B read per edge, 2 B scattered write per
-// machine arc).  The [2,E] rows are 16-byte aligned when E is even; a scalar tail handles the rest.
-__global__ void __launch_bounds__(512) coo_ingest_kernel(const __grid_constant__ CooIngestArgs a) {
+// Each thread takes kIngestTrips x 2 edges as 16-byte loads from both rows of the [2,E] list, all issued before the
+// first use: the kernel is a pure HBM stream (16 B read per edge, 2 B scattered write per machine arc).  The rows
+// are 16-byte aligned when E is even; otherwise (or for a misaligned view) every thread takes single edges.
+constexpr int kIngestTrips = 4;
+__global__ void __launch_bounds__(256) coo_ingest_kernel(const __grid_constant__ CooIngestArgs a) {
   int conj = 0, bad = 0;
-  const long long E = a.E;
-  const bool vec_ok = (E % 2 == 0) && ((reinterpret_cast<unsigned long long>(a.ei) & 15ull) == 0);
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
-  long long done_upto = 0;
-  if (vec_ok) {
+  const unsigned E = (unsigned)a.E;
+  const unsigned tid0 = blockIdx.x * (256u * kIngestTrips) + threadIdx.x;
+  if (a.vec_ok) {
     const longlong2* us = reinterpret_cast<const longlong2*>(a.ei);
-    const longlong2* vs = reinterpret_cast<const longlong2*>(a.ei + E);
-    const long long E2 = E / 2;
-#pragma unroll 2
-    for (long long e = tid; e < E2; e += nthr) {
-      const longlong2 u = us[e], v = vs[e];
-      const int r0 = coo_edge(a, u.x, v.x), r1 = coo_edge(a, u.y, v.y);
-      conj += (r0 > 0) + (r1 > 0);
-      bad |= (r0 < 0) | (r1 < 0);
+    const longlong2* vs = reinterpret_cast<const longlong2*>(a.ei + a.E);
+    const unsigned E2 = E >> 1;
+    longlong2 u[kIngestTrips], v[kIngestTrips];
+#pragma unroll
+    for (int k = 0; k < kIngestTrips; ++k) {
+      const unsigned e = tid0 + 256u * k;
+      if (e < E2) { u[k] = us[e]; v[k] = vs[e]; }
     }
-    done_upto = E;
-  }
-  for (long long e = done_upto + tid; e < E; e += nthr) {
-    const int r = coo_edge(a, a.ei[e], a.ei[E + e]);
-    conj += r > 0;
-    bad |= r < 0;
+#pragma unroll
+    for (int k = 0; k < kIngestTrips; ++k) {
+      const unsigned e = tid0 + 256u * k;
+      if (e < E2) {
+        const int r0 = coo_edge(a, u[k].x, v[k].x), r1 = coo_edge(a, u[k].y, v[k].y);
+        conj += (r0 > 0) + (r1 > 0);
+        bad |= (r0 < 0) | (r1 < 0);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kIngestTrips; ++k) {
+      const unsigned e = tid0 + 256u * k;
+      if (e < E) {
+        const int r = coo_edge(a, a.ei[e], a.ei[a.E + e]);
+        conj += r > 0;
+        bad |= r < 0;
+      }
+    }
   }
   if (bad) atomicCAS(a.ws.flag, 0, -5);
   // one atomic per CTA
-  __shared__ int warp_sums[32];
+  __shared__ int warp_sums[8];
   for (int o = 16; o; o >>= 1) conj += __shfl_xor_sync(kFull, conj, o);
   if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = conj;
   __syncthreads();
   if (threadIdx.x < 32) {
-    int t = threadIdx.x < (blockDim.x >> 5) ? warp_sums[threadIdx.x] : 0;
-    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+    int t = threadIdx.x < 8 ? warp_sums[threadIdx.x] : 0;
+    for (int o = 4; o; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
     if (threadIdx.x == 0 && t) atomicAdd(a.ws.conj_count, (unsigned long long)t);
   }
 }
