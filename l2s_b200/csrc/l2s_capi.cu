@@ -516,7 +516,8 @@ int l2s_poll_error(l2s_handle h, int* instance_out, void* stream) {
 int64_t l2s_eval_coo_workspace_bytes(int n_j, int n_m, int64_t batch) {
   if (n_j < 1 || n_m < 1 || batch < 1) return L2S_ERR_INVALID_ARG;
   const long long node_stride = ru((long long)n_j * n_m + 2, 8);
-  return batch * node_stride * 2 + 16;
+  const long long n1p = ru((long long)n_j * n_m + 2, 4);
+  return batch * node_stride * 2 + 16 + 2 * n1p * 4;
 }
 
 int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duration, int duration_is_i64, int n_j,
@@ -543,6 +544,7 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   const size_t links = (size_t)batch * L.node_stride * 2;
   a.ws.msucc = (uint16_t*)workspace;
   a.ws.conj_count = (unsigned long long*)((char*)workspace + links);
+  a.ws.pending_page = (int32_t*)((char*)workspace + links + 16);
   a.ws.flag = status_flag;
   a.est = est; a.lst = lst; a.ms = makespan;
   a.expect_conj = batch * ((long long)n_j * (n_m + 1));
@@ -551,6 +553,7 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   a.off_durw = off;  off += L.node_stride * 2;
   a.off_succ = off;  off += L.node_stride * 2;
   a.off_heads = off; off += 64;
+  a.off_bar = off;   off += 16;
   a.bytes = ru(off, 16);
   const int W = pick_warps(a.bytes, 4);
   if (!W) return L2S_ERR_UNSUPPORTED_SHAPE;
@@ -569,6 +572,7 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   g.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   g.ws = a.ws;
   g.lim = (unsigned)(batch * (n + 2));
+  g.page_words = 2 * L.n1p;
   g.vec_ok = (n_edges % 2 == 0) && (((unsigned long long)edge_index & 15ull) == 0);
   const long long items = g.vec_ok ? n_edges / 2 : n_edges;           // loads per row
   long long blocks = (items + 256 * kIngestTrips - 1) / (256 * kIngestTrips);

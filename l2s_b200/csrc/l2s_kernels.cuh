@@ -839,6 +839,7 @@ struct CooWs {
   uint16_t* msucc;      // [B][node_stride]
   unsigned long long* conj_count;
   int32_t* flag;        // device status word
+  int32_t* pending_page; // [2*n1p] words of -1 (written by the ingest kernel): TMA source for the tq sentinels
 };
 
 struct CooIngestArgs {
@@ -847,6 +848,7 @@ struct CooIngestArgs {
   int n_j, n_m, n, n1, node_stride;
   unsigned magic_n1, magic_nm;   // floor(2^32 / d) + 1, see fast_div
   unsigned lim;                  // batch * (n+2)
+  int page_words;                // 2*n1p
   int vec_ok;                    // rows 16-byte aligned and E even: 2 edges per load
   CooWs ws;
 };
@@ -929,6 +931,8 @@ __global__ void __launch_bounds__(256) coo_ingest_kernel(const __grid_constant__
     }
   }
   if (bad) atomicCAS(a.ws.flag, 0, -5);
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < a.page_words; i += 256) a.ws.pending_page[i] = -1;
   // one atomic per CTA
   __shared__ int warp_sums[8];
   for (int o = 16; o; o >>= 1) conj += __shfl_xor_sync(kFull, conj, o);
@@ -951,7 +955,7 @@ struct CooEvalArgs {
   float* lst;
   float* ms;
   int bytes;           // smem per graph
-  int off_durw, off_succ, off_heads;
+  int off_durw, off_succ, off_heads, off_bar;
   long long expect_conj;
 };
 
@@ -968,9 +972,15 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   const int n = L.n, n1 = L.n1, n_m = L.n_m, n_j = L.n_j;
   if (b == 0 && lane == 0 && *a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
 
-  // stage: machine successors (uint16, 16-byte vectors) and durations -> node words
-  const uint4* gs = reinterpret_cast<const uint4*>(a.ws.msucc + b * L.node_stride);
-  for (int i = lane; i < L.node_stride / 8; i += 32) sts128(succ + 16 * i, gs[i]);
+  // stage: machine successors and the "pending" sentinels by TMA bulk copies (one lane), durations -> node words
+  const uint32_t bar = base + a.off_bar;
+  if (lane == 0) {
+    const uint32_t sbytes = (uint32_t)L.node_stride * 2u, tbytes = 2u * (uint32_t)L.n1p * 4u;
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, sbytes + tbytes);
+    bulk_g2s(succ, a.ws.msucc + b * L.node_stride, sbytes, bar);
+    bulk_g2s(s.tq, a.ws.pending_page, tbytes, bar);
+  }
   int bad = 0;
   {
     int pos = lane == 0 ? n_m - 1 : (lane - 1) % n_m;   // (i-1) mod n_m, advanced by 32 per trip
@@ -987,8 +997,8 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
       if (pos >= n_m) pos -= n_m;
     }
   }
-  fill_pending(L, s, lane, true);
   __syncwarp();
+  mbar_wait(bar, 0);
   // heads = operations nobody points to.  Mark successors in tq's (still unused) backward half as a bitmap.
   const uint32_t bits = s.tq + 4u * L.n1p;          // reuse: n1 bits <= 4*n1p bytes
   for (int i = lane; i < (n1 + 31) / 32; i += 32) sts32(bits + 4u * i, 0);
@@ -1029,7 +1039,7 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
     if (v != 0) chain_ok = 0;      // longer than n_j (or a cycle)
   }
   chain_ok = __reduce_and_sync(kFull, chain_ok);
-  fill_pending(L, s, lane, true);  // the bitmap lived in the backward half
+  for (int i = lane; i < (n1 + 31) / 32; i += 32) sts32(bits + 4u * i, -1);   // the bitmap lived in the backward half
   __syncwarp();
   const int ms = chain_ok ? evaluate_instance(L, s, lane, true) : -1;
   if (ms < 0) {
