@@ -29,7 +29,7 @@ inline int ru(long long x, int a) { return (int)((x + a - 1) / a * a); }
     }                                                                                             \
   } while (0)
 
-Layout make_layout(int n_j, int n_m) {
+Layout make_layout(int n_j, int n_m, bool stage_durw = false) {
   Layout L;
   memset(&L, 0, sizeof(L));
   L.n_j = n_j;
@@ -46,10 +46,10 @@ Layout make_layout(int n_j, int n_m) {
   L.off_walk = off; off += L.walk_stride * 4;
   L.off_crit = off; off += L.node_stride * 2;
   L.off_misc = off; off += 16;
-  // small instances keep the static node words in shared memory too (cheaper feature loop); large ones read them
-  // from HBM so that one more instance fits an SM
+  // small instances (warp-per-instance step kernel) keep the static node words in shared memory too (cheaper
+  // feature loop); large ones (CTA-per-instance kernel) read them from HBM so that one more instance fits an SM
   L.off_durw = -1;
-  if ((size_t)ru(off, 16) + (size_t)L.node_stride * 2 + kSmemCtaReserve <= kSmemPerSm / 16) {
+  if (stage_durw) {
     L.off_durw = off;
     off += L.node_stride * 2;
   }
@@ -159,7 +159,11 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->device = device;
   h->B = batch;
   h->pmax = pmax;
-  h->L = make_layout(n_j, n_m);
+  // kernel + layout choice: the warp-per-instance step kernel (with staged node words) if at least 16 such
+  // instances fit an SM, else one CTA per instance
+  h->L = make_layout(n_j, n_m, true);
+  const bool small = (long long)(kSmemPerSm / ((size_t)h->L.bytes + kSmemCtaReserve)) >= 16;
+  if (!small) h->L = make_layout(n_j, n_m, false);
   const Layout& L = h->L;
   h->run_off_where = L.bytes;
   h->run_off_plist = L.bytes + L.node_stride * 2;
@@ -186,8 +190,11 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   // few instances per SM (large graphs): give every instance a whole CTA so that the SM is not left idle
   {
     const long long per_sm = (long long)(kSmemPerSm / ((size_t)L.bytes + kSmemCtaReserve));
-    h->cta_warps = per_sm < 16 ? (per_sm <= 4 ? 8 : 4) : 0;   // measured: 150x25 best at 8, 100x20 / 50x20 at 4, 30x20 warp-per-instance
-    if (const char* e = getenv("L2S_CTA_WARPS")) h->cta_warps = atoi(e);
+    h->cta_warps = small ? 0 : (per_sm <= 4 ? 8 : 4);   // measured: 150x25 best at 8, 100x20 / 50x20 at 4, 30x20 warp-per-instance
+    if (const char* e = getenv("L2S_CTA_WARPS")) {      // experiments: force the CTA kernel (0 keeps the choice above)
+      const int v = atoi(e);
+      if (v > 0) { h->cta_warps = v; }
+    }
     if (h->cta_warps > 8) h->cta_warps = 8;
   }
   CU(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax - 1024));   // it also has static shared memory

@@ -300,7 +300,9 @@ struct StepArgs {
   int32_t* ex_path_len;
 };
 
-// <= 4 warps per CTA, >= 8 CTAs per SM: 64 registers (measured best: the kernel is issue-bound, not occupancy-bound)
+// Warp-per-instance step for instances of which >= 16 fit an SM; the static node words are always staged in
+// shared memory here (l2s_create picks the layout together with the kernel).
+// <= 4 warps per CTA, >= 8 CTAs per SM: 64 registers (measured: the kernel is issue-bound, not occupancy-bound)
 __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_step[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -364,8 +366,6 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     }
     return;
   }
-  const uint16_t* gdurw = a.st.durw + (size_t)b * L.node_stride;   // static node words (large instances)
-  const bool sm_dur = L.off_durw >= 0;
   const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   // latest start of S = min over job-first ops (:195 on the S row)
   int qs = 0;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
       // common case: one FMA residual correction reproduces the IEEE quotient (verified on the host)
       const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
       for (int i = lane; i < n1; i += 32, xo += 96) {
-        const int d = (sm_dur ? lds16(s.durw + 2u * i) : (int)__ldg(gdurw + i)) & kDurMask;
+        const int d = lds16(s.durw + 2u * i) & kDurMask;
         const float fd = (float)d, fe = (float)(lds32(fin + 4u * i) - d), fl = fms - (float)lds32(q + 4u * i);
         float q0 = __fmul_rn(fd, rh), q1 = __fmul_rn(fe, rf), q2 = __fmul_rn(fl, rf);
         xo[0] = __fmaf_rn(__fmaf_rn(-ch, q0, fd), rh, q0);
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
       }
     } else {
       for (int i = lane; i < n1; i += 32, xo += 96) {
-        const int d = (sm_dur ? lds16(s.durw + 2u * i) : (int)__ldg(gdurw + i)) & kDurMask;
+        const int d = lds16(s.durw + 2u * i) & kDurMask;
         const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
         xo[0] = div_rn((float)d, a.high, a.r_high, a.div_high);
         xo[1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   }
   if (a.ex_est) {
     for (int i = lane; i < n1; i += 32) {
-      const int d = __ldg(gdurw + i) & kDurMask;
+      const int d = lds16(s.durw + 2u * i) & kDurMask;
       a.ex_est[(size_t)b * n1 + i] = lds32(fin + 4u * i) - d;
       a.ex_lst[(size_t)b * n1 + i] = ms - lds32(q + 4u * i);
     }
