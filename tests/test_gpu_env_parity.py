@@ -225,3 +225,38 @@ def test_device_api_errors_are_reported_asynchronously():
     tape[3, 2] = [7, 7]
     with pytest.raises(nx.NetworkXError):
         env2.run("replay", 5, tape=tape)
+
+
+def test_plain_c_host_through_the_c_abi(tmp_path):
+    """examples/capi_demo.c: a C program that links libl2s_b200.so and drives reset + steps with host buffers gives
+    the same makespans / move counts / features as the Python drop-in on the same instances."""
+    import re
+    import subprocess
+    from conftest import ROOT
+    from l2s_b200 import JsspN5, build
+    exe = str(tmp_path / "capi_demo")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["gcc", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(ROOT, "examples", "capi_demo.c"), "-o", exe, "-L", build.LIB_DIR, "-ll2s_b200",
+           "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + build.LIB_DIR]
+    subprocess.run(cmd, check=True, capture_output=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.strip().endswith("ok")
+    dur = np.array([[5, 3, 7, 2, 8, 4, 6, 1, 9, 3, 3, 5], [4, 4, 2, 9, 1, 6, 3, 7, 5, 2, 8, 6]]).reshape(2, 4, 3)
+    mch = np.array([[1, 2, 3, 2, 1, 3, 3, 1, 2, 1, 3, 2], [2, 3, 1, 1, 2, 3, 3, 2, 1, 2, 1, 3]]).reshape(2, 4, 3)
+    env = JsspN5(4, 3, 1, 99)
+    state, fa, done = env.reset(np.stack([dur, mch], axis=1), "fdd-divide-mwkr", "cuda")
+    lines = out.strip().split("\\n")
+    m = re.match(r"reset: makespans (\\d+) (\\d+), moves (\\d+) (\\d+)", lines[0])
+    assert [int(v) for v in m.groups()[:2]] == env.current_objs.reshape(-1).int().tolist()
+    for k in range(6):
+        acts = [f[0] for f in fa]
+        state, r, fa, done = env.step(acts, "cuda")
+        m = re.match(r"step \\d+: actions \\((\\d+),(\\d+)\\) \\((\\d+),(\\d+)\\) -> makespans (\\d+) (\\d+), rewards (\\d+) (\\d+), moves (\\d+) (\\d+)",
+                     lines[1 + k])
+        g = [int(v) for v in m.groups()]
+        assert [g[0:2], g[2:4]] == acts
+        assert g[4:6] == env.current_objs.reshape(-1).int().tolist() and g[6:8] == r.reshape(-1).int().tolist()
+        assert g[8:10] == [0 if f == [[0, 0]] else len(f) for f in fa]
+    x1 = [float(v) for v in lines[-2].split("=")[1].split()]
+    assert np.allclose(x1, state[0][1].cpu().numpy(), atol=1e-6)
