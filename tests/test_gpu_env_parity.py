@@ -246,13 +246,13 @@ def test_plain_c_host_through_the_c_abi(tmp_path):
     mch = np.array([[1, 2, 3, 2, 1, 3, 3, 1, 2, 1, 3, 2], [2, 3, 1, 1, 2, 3, 3, 2, 1, 2, 1, 3]]).reshape(2, 4, 3)
     env = JsspN5(4, 3, 1, 99)
     state, fa, done = env.reset(np.stack([dur, mch], axis=1), "fdd-divide-mwkr", "cuda")
-    lines = out.strip().split("\\n")
-    m = re.match(r"reset: makespans (\\d+) (\\d+), moves (\\d+) (\\d+)", lines[0])
+    lines = out.strip().split("\n")
+    m = re.match(r"reset: makespans (\d+) (\d+), moves (\d+) (\d+)", lines[0])
     assert [int(v) for v in m.groups()[:2]] == env.current_objs.reshape(-1).int().tolist()
     for k in range(6):
         acts = [f[0] for f in fa]
         state, r, fa, done = env.step(acts, "cuda")
-        m = re.match(r"step \\d+: actions \\((\\d+),(\\d+)\\) \\((\\d+),(\\d+)\\) -> makespans (\\d+) (\\d+), rewards (\\d+) (\\d+), moves (\\d+) (\\d+)",
+        m = re.match(r"step \d+: actions \((\d+),(\d+)\) \((\d+),(\d+)\) -> makespans (\d+) (\d+), rewards (\d+) (\d+), moves (\d+) (\d+)",
                      lines[1 + k])
         g = [int(v) for v in m.groups()]
         assert [g[0:2], g[2:4]] == acts
