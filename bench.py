@@ -12,8 +12,9 @@ A "step" is ONE `l2s_step` launch over one batch: swap + re-evaluation (est, lst
 machine edges + reward/incumbent/tabu + critical path + N5 move set for every instance of the batch.
 
   value : device-resident throughput (state and action tape already in HBM), CUDA events, max over ranks.
-  e2e   : the same steps through the C-ABI `l2s_step_host` with HOST buffers: host actions in, pinned H2D copy,
-          kernel, D2H of move sets / rewards / makespans, host arrays out, stream synchronised every step.
+  e2e   : the same steps through the C-ABI `l2s_step_host` with HOST buffers: the kernel reads the host actions
+          over PCIe from pinned memory and writes one result record per instance (move set, reward, makespan,
+          incumbent, done, status) over PCIe into pinned host memory; stream synchronised every step.
   e2e_python_api : the same through the drop-in `JsspN5.step(actions, device)` (Python lists in and out).
   evaluator : `Evaluator.forward` on the int64 COO edge lists of the same schedules (graphs/s, GB/s).
   roofline : algorithmic bytes of one step (SURVEY.md 8d formula) / mean launch duration vs measured HBM peak.
@@ -308,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
         r = k % REPLICAS
         hb.append((r, np.ascontiguousarray(host_tapes[r][p3[r]])))
         p3[r] += 1
-    # host results are read in place from the handle's pinned buffers (l2s_host_buffers): zero extra copies
+    # host results are read in place from the handle's pinned records (l2s_host_records): zero extra copies
     sink = 0
 
     def capi_step(r, acts):
@@ -319,7 +320,7 @@ def run_ours(args, rank, world, local_rank):
                           pairs=None, npairs=None, status=None)
         _capi.check(lib.l2s_step_host(envs[r]._h, C.byref(io), acts.ctypes.data, None, None, None, None, None,
                                       None, sp), "l2s_step_host")
-        return int(envs[r]._h_npairs[0]) + int(envs[r]._h_status[0])     # touch the host results
+        return int(envs[r]._h_rec[0, 0]) + int(envs[r]._h_rec[-1, 0])     # touch the host results
 
     for r, acts in hb[:w_e2e]:
         capi_step(r, acts)
@@ -329,7 +330,7 @@ def run_ours(args, rank, world, local_rank):
         capi_step(r, acts)
     torch.cuda.synchronize(dev)
     t_capi = time.perf_counter() - t0
-    assert not any(e._h_status.any() for e in envs)
+    assert not any((e._h_rec[:, 0] >> 24).any() for e in envs)
 
     # ---- phase 4: stateless evaluator (Evaluator.forward drop-in) on the current schedules ----------------
     from l2s_b200 import Evaluator
@@ -414,8 +415,10 @@ def run_ours(args, rank, world, local_rank):
                              % (REPLICAS, REPLICAS),
                        "mean_pairs": pbar, "parallelism": "instance-sharded x%d" % world},
             "e2e": {"value": e2e_capi, "unit": UNIT,
-                    "api": "C-ABI l2s_step_host: host int32 actions in, host pairs/npairs/done/reward/makespan/status out",
-                    "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": int(envs[0]._lib.l2s_pmax(envs[0]._h)) * B * 4 + B * 21,
+                    "api": "C-ABI l2s_step_host: host int32 actions in (read in place from pinned memory by the kernel), "
+                           "host records out (pairs/npairs/done/reward/makespan/incumbent/status, written into pinned "
+                           "memory by the kernel), sync per step",
+                    "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": int(B * (16 + 4 * pbar)),
                     "steps": K},
             "e2e_python_api": {"value": e2e_py, "unit": UNIT,
                                "api": "drop-in JsspN5.step(actions: list[B][2], device) -> (state, reward, list[B][P][2], done); "

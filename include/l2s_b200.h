@@ -116,21 +116,32 @@ typedef struct {
  * reward/incumbent/tabu update, critical path, N5 move set. */
 int l2s_step(l2s_handle h, const l2s_step_io* io, void* stream);
 
-/* Same step driven from HOST memory: copies `actions_host` ([batch,2] int32, may be NULL) to the device,
- * runs l2s_step with the device outputs in `io` (io->actions is ignored), copies the move sets back and
- * synchronises the stream.  Host outputs may be NULL (read the pinned views of l2s_host_buffers instead).
- * pairs_host is [batch,pmax,2] int32; only the first npairs_host[b] pairs of row b are written. */
+/* Same step driven from HOST memory (the call the Python drop-in's JsspN5.step makes, env/environment.py:356-387).
+ * `actions_host` ([batch,2] int32, may be NULL = evaluate only) is read by the kernel in place from pinned host
+ * memory (it is first copied into the handle's pinned buffer unless it already is that buffer); the device
+ * outputs in `io` are written as in l2s_step (io->actions is ignored); the per-instance host results -- move set,
+ * counts, reward, makespan, incumbent, done, status -- are written BY THE KERNEL as one coalesced record per
+ * instance straight into mapped pinned host memory (l2s_host_records), so that a step needs no copy call; the
+ * stream is synchronised before returning.  The optional host output arrays are unpacked from the records on the
+ * host; pass NULL and read the records in place to skip that.  pairs_host is [batch,pmax,2] int32; only the
+ * first npairs_host[b] pairs of row b are written. */
 int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_host, int32_t* pairs_host,
                   int32_t* npairs_host, uint8_t* done_host, float* reward_host, float* makespan_host,
                   int32_t* status_host, void* stream);
 
-/* Pinned host buffers that l2s_step_host fills (zero-copy views for a binding; any out-pointer may be
- * NULL): pairs16 [batch,pmax,2] uint16 (node ids fit 16 bits; only the first npairs[b] pairs of row b are
- * defined), npairs/status [batch] int32, reward/makespan/incumbent [batch] float, done [batch] uint8, and the
- * pinned action staging buffer [batch,2] int32 (write actions there and pass the same pointer as
- * actions_host to skip a host copy). */
-int l2s_host_buffers(l2s_handle h, uint16_t** pairs16, int32_t** npairs, int32_t** status, float** reward,
-                     float** makespan, float** incumbent, uint8_t** done, int32_t** actions);
+/* Host result records of l2s_step_host: `records` is [batch][stride_words] uint32 in pinned host memory owned by
+ * the handle, stride_words = L2S_REC_HEADER_WORDS + pmax.  Record of instance b:
+ *   word 0      npairs (bits 0-15) | done (bit 16) | per-instance l2s_status as int8 (bits 24-31)
+ *   word 1..3   makespan, reward, incumbent as float32 bit patterns
+ *   word 4+i    feasible pair i (i < npairs) in critical-path order: a0 | a1 << 16 (node ids fit 16 bits);
+ *               words beyond npairs are stale
+ * `actions` is the pinned action staging buffer [batch,2] int32: write actions there and pass the same pointer
+ * as actions_host to skip a host copy.  Any out-pointer may be NULL. */
+#define L2S_REC_HEADER_WORDS 4
+#define L2S_REC_NPAIRS(w0) ((w0) & 0xffffu)
+#define L2S_REC_DONE(w0) (((w0) >> 16) & 1u)
+#define L2S_REC_STATUS(w0) ((int)(int8_t)((w0) >> 24))
+int l2s_host_records(l2s_handle h, const uint32_t** records, int* stride_words, int32_t** actions);
 
 /* K fused steps in ONE launch with an on-device policy; the search state never leaves shared memory.
  *   REPLAY: tape [batch, K, 2] int32 actions.

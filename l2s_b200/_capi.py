@@ -11,6 +11,8 @@ c_i32p = C.POINTER(C.c_int32)
 c_f32p = C.POINTER(C.c_float)
 c_u8p = C.POINTER(C.c_uint8)
 c_u16p = C.POINTER(C.c_uint16)
+c_u32p = C.POINTER(C.c_uint32)
+REC_HEADER_WORDS = 4   # L2S_REC_HEADER_WORDS: host record = [npairs | done<<16 | status<<24, makespan, reward, incumbent, pairs...]
 
 
 class L2SError(RuntimeError):
@@ -55,9 +57,7 @@ PROTOTYPES = {
     "l2s_step": (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p]),
     "l2s_step_host": (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "l2s_host_buffers": (C.c_int, [C.c_void_p, C.POINTER(c_u16p), C.POINTER(c_i32p), C.POINTER(c_i32p),
-                                   C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_f32p), C.POINTER(c_u8p),
-                                   C.POINTER(c_i32p)]),
+    "l2s_host_records": (C.c_int, [C.c_void_p, C.POINTER(c_u32p), c_i32p, C.POINTER(c_i32p)]),
     "l2s_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, c_i32p, C.c_int,
                           C.c_void_p, C.c_void_p]),
     "l2s_export_state": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_void_p]),
@@ -114,7 +114,7 @@ def pylists():
         try:
             L = C.PyDLL(path)
             L.l2s_build_move_lists.restype = C.py_object
-            L.l2s_build_move_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+            L.l2s_build_move_lists.argtypes = [C.c_void_p, C.c_int, C.c_int]
             L.l2s_parse_actions.restype = C.c_int
             L.l2s_parse_actions.argtypes = [C.py_object, C.c_void_p, C.c_int]
             _pylists = L

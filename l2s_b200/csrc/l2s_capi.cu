@@ -29,7 +29,7 @@ inline int ru(long long x, int a) { return (int)((x + a - 1) / a * a); }
     }                                                                                             \
   } while (0)
 
-Layout make_layout(int n_j, int n_m, bool stage_durw = false) {
+Layout make_layout(int n_j, int n_m, bool stage_durw = false, int pmax = 0) {
   Layout L;
   memset(&L, 0, sizeof(L));
   L.n_j = n_j;
@@ -52,6 +52,13 @@ Layout make_layout(int n_j, int n_m, bool stage_durw = false) {
   if (stage_durw) {
     L.off_durw = off;
     off += L.node_stride * 2;
+  }
+  // host record staging (4 + pmax words): the critical-predecessor array is dead by then; tiny instances get
+  // their own region
+  L.off_rec = L.off_crit;
+  if ((4 + pmax) * 4 > L.node_stride * 2) {
+    L.off_rec = off;
+    off += ru((4 + pmax) * 4, 16);
   }
   L.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   L.bytes = ru(off, 16);
@@ -111,20 +118,21 @@ struct l2s_handle_s {
   size_t run_stride;
   int run_off_where, run_off_plist;
   InitLayout IL;
-  // staging for the host-driven step
+  // host-driven step: pinned action staging and the per-instance result records
   int32_t* d_actions;
-  int32_t* h_actions;     // pinned
-  unsigned char* d_pack;
-  unsigned char* h_pack;  // pinned
-  size_t pack_bytes;
-  size_t off_npairs, off_status, off_reward, off_ms, off_inc, off_done, off_pairs;
+  int32_t* h_actions;          // pinned + mapped
+  int32_t* h_actions_dev;      // device-side address of h_actions
+  uint32_t* h_rec;             // pinned + mapped: [B][4 + pmax] words, written by the step kernel
+  uint32_t* h_rec_dev;         // device-side address of h_rec
+  uint32_t* d_rec;             // device staging, only for rec_direct == 0
+  size_t rec_bytes;
   // divisors already verified for the FMA division (x features)
   float div_c[2], div_r[2];
   int div_mode[2];
-  // zero-copy host path: the kernel reads actions from / writes results to mapped pinned host memory directly
+  // zero-copy host path (defaults 1/1; L2S_HOST_ZEROCOPY=0 stages the actions with an H2D copy,
+  // L2S_HOST_RECORDS=0 writes the records to device memory and copies them back with one bulk D2H)
   int zero_copy;
-  unsigned char* h_pack_dev;   // device-side address of h_pack
-  int32_t* h_actions_dev;      // device-side address of h_actions
+  int rec_direct;
 };
 
 extern "C" {
@@ -161,9 +169,9 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->pmax = pmax;
   // kernel + layout choice: the warp-per-instance step kernel (with staged node words) if at least 16 such
   // instances fit an SM, else one CTA per instance
-  h->L = make_layout(n_j, n_m, true);
+  h->L = make_layout(n_j, n_m, true, pmax);
   const bool small = (long long)(kSmemPerSm / ((size_t)h->L.bytes + kSmemCtaReserve)) >= 16;
-  if (!small) h->L = make_layout(n_j, n_m, false);
+  if (!small) h->L = make_layout(n_j, n_m, false, pmax);
   const Layout& L = h->L;
   h->run_off_where = L.bytes;
   h->run_off_plist = L.bytes + L.node_stride * 2;
@@ -230,26 +238,23 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   CU(cudaMemset(st.cur, 0, B * 4));
   CU(cudaMemset(st.inc, 0, B * 4));
   CU(cudaMemset(st.err, 0, 4));
-  // host-step staging: one packed result block so that a step needs a single D2H copy
-  size_t off = 0;
-  h->off_npairs = off; off += ru(B * 4, 16);
-  h->off_status = off; off += ru(B * 4, 16);
-  h->off_reward = off; off += ru(B * 4, 16);
-  h->off_ms = off;     off += ru(B * 4, 16);
-  h->off_inc = off;    off += ru(B * 4, 16);
-  h->off_done = off;   off += ru(B, 16);
-  h->off_pairs = off;  off += ru(B * pmax * 4, 16);   // uint16 pairs
-  h->pack_bytes = off;
-  CU(cudaMalloc(&h->d_pack, h->pack_bytes));
-  CU(cudaMemset(h->d_pack, 0, h->pack_bytes));
-  CU(cudaMallocHost(&h->h_pack, h->pack_bytes));
-  memset(h->h_pack, 0, h->pack_bytes);
+  // host-step staging.  Measured on B200 (20x15, 8192 instances per step): records written by the kernel straight
+  // into mapped host memory (one coalesced store of 16 + 4*npairs bytes per instance, overlapping the rest of the
+  // launch) 57 us per step; packed SoA block + one bulk D2H 84 us; scattered 4-byte zero-copy stores: slower still.
+  h->rec_bytes = B * (size_t)(4 + pmax) * 4;
+  CU(cudaHostAlloc((void**)&h->h_rec, h->rec_bytes, cudaHostAllocMapped));
+  memset(h->h_rec, 0, h->rec_bytes);
+  CU(cudaHostGetDevicePointer((void**)&h->h_rec_dev, h->h_rec, 0));
+  CU(cudaMalloc(&h->d_rec, h->rec_bytes));
+  CU(cudaMemset(h->d_rec, 0, h->rec_bytes));
   CU(cudaMalloc(&h->d_actions, B * 8));
-  CU(cudaMallocHost(&h->h_actions, B * 8));
-  CU(cudaHostGetDevicePointer((void**)&h->h_pack_dev, h->h_pack, 0));
+  CU(cudaHostAlloc((void**)&h->h_actions, B * 8, cudaHostAllocMapped));
+  memset(h->h_actions, 0, B * 8);
   CU(cudaHostGetDevicePointer((void**)&h->h_actions_dev, h->h_actions, 0));
-  h->zero_copy = 2;   // measured: actions read in place (+12 % e2e); streaming results over PCIe from the kernel is slower than one bulk D2H
-  if (const char* e = getenv("L2S_HOST_ZEROCOPY")) h->zero_copy = atoi(e);
+  h->zero_copy = 1;
+  h->rec_direct = 1;
+  if (const char* e = getenv("L2S_HOST_ZEROCOPY")) h->zero_copy = atoi(e) != 0;
+  if (const char* e = getenv("L2S_HOST_RECORDS")) h->rec_direct = atoi(e) != 0;
   *out = h;
   return L2S_OK;
 }
@@ -260,7 +265,7 @@ int l2s_destroy(l2s_handle h) {
   cudaFree(h->st.durw); cudaFree(h->st.mch); cudaFree(h->st.walk); cudaFree(h->st.where);
   cudaFree(h->st.tabu); cudaFree(h->st.cur); cudaFree(h->st.inc); cudaFree(h->st.err);
   cudaFree((void*)h->st.pending_page);
-  cudaFree(h->d_pack); cudaFreeHost(h->h_pack); cudaFree(h->d_actions); cudaFreeHost(h->h_actions);
+  cudaFree(h->d_rec); cudaFreeHost(h->h_rec); cudaFree(h->d_actions); cudaFreeHost(h->h_actions);
   free(h);
   return L2S_OK;
 }
@@ -372,16 +377,10 @@ int l2s_step(l2s_handle h, const l2s_step_io* io, void* stream) {
   return r;
 }
 
-int l2s_host_buffers(l2s_handle h, uint16_t** pairs16, int32_t** npairs, int32_t** status, float** reward,
-                     float** makespan, float** incumbent, uint8_t** done, int32_t** actions) {
+int l2s_host_records(l2s_handle h, const uint32_t** records, int* stride_words, int32_t** actions) {
   if (!h) return L2S_ERR_INVALID_ARG;
-  if (pairs16) *pairs16 = (uint16_t*)(h->h_pack + h->off_pairs);
-  if (npairs) *npairs = (int32_t*)(h->h_pack + h->off_npairs);
-  if (status) *status = (int32_t*)(h->h_pack + h->off_status);
-  if (reward) *reward = (float*)(h->h_pack + h->off_reward);
-  if (makespan) *makespan = (float*)(h->h_pack + h->off_ms);
-  if (incumbent) *incumbent = (float*)(h->h_pack + h->off_inc);
-  if (done) *done = (uint8_t*)(h->h_pack + h->off_done);
+  if (records) *records = h->h_rec;
+  if (stride_words) *stride_words = L2S_REC_HEADER_WORDS + h->pmax;
   if (actions) *actions = h->h_actions;
   return L2S_OK;
 }
@@ -396,52 +395,45 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
   const size_t B = h->B;
   StepArgs a = step_args(h, io);
   a.actions = nullptr;
-  // Host path.  zero_copy = 2 (default): the kernel reads the 8-byte actions straight from mapped pinned host
-  // memory (no H2D copy call); results come back with ONE bulk D2H of the packed block.  zero_copy = 1 also
-  // streams the results to host memory from inside the kernel (measured slower: many small PCIe writes);
-  // zero_copy = 0 stages both directions.  L2S_HOST_ZEROCOPY overrides.
-  const bool zc = h->zero_copy == 1 && !io->npairs && !io->status;   // results straight to host memory
-  const bool zc_act = h->zero_copy >= 1;                              // actions straight from host memory
-  unsigned char* pack = zc ? h->h_pack_dev : h->d_pack;
+  // Host path: the kernel reads the 8-byte actions straight from mapped pinned host memory and writes one
+  // coalesced result record per instance straight back into mapped pinned host memory: no copy calls at all,
+  // the PCIe traffic overlaps the launch.  (L2S_HOST_ZEROCOPY=0 / L2S_HOST_RECORDS=0 stage through device
+  // memory with explicit copies instead.)
   if (actions_host) {
     if (actions_host != h->h_actions) memcpy(h->h_actions, actions_host, B * 8);
-    if (zc_act) {
+    if (h->zero_copy) {
       a.actions = h->h_actions_dev;
     } else {
       CU(cudaMemcpyAsync(h->d_actions, h->h_actions, B * 8, cudaMemcpyHostToDevice, s));
       a.actions = h->d_actions;
     }
   }
-  // results the host needs go to the packed block; per-instance scalars are mirrored there by the kernel
-  a.pairs = io->pairs;                            // optional int32 device copy for the caller
-  a.pairs16 = (uint16_t*)(pack + h->off_pairs);   // packed copy for the host
-  a.npairs = (int32_t*)(pack + h->off_npairs);
-  a.status = (int32_t*)(pack + h->off_status);
-  a.reward2 = (float*)(pack + h->off_reward);
-  a.makespan2 = (float*)(pack + h->off_ms);
-  a.incumbent2 = (float*)(pack + h->off_inc);
-  a.done2 = (uint8_t*)(pack + h->off_done);
+  a.rec = h->rec_direct ? h->h_rec_dev : h->d_rec;
+  a.rec_stride = L2S_REC_HEADER_WORDS + h->pmax;
   int r = launch_step(h, a, stream);
   if (r != L2S_OK) return r;
   if (!io->is_reset && a.actions) h->itr += 1;
-  if (!zc) CU(cudaMemcpyAsync(h->h_pack, h->d_pack, h->pack_bytes, cudaMemcpyDeviceToHost, s));
+  if (!h->rec_direct) CU(cudaMemcpyAsync(h->h_rec, h->d_rec, h->rec_bytes, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  if (pairs_host) {   // widen the packed uint16 pairs; only the valid prefix of every row is defined
-    const uint16_t* p16 = (const uint16_t*)(h->h_pack + h->off_pairs);
-    const int32_t* np = (const int32_t*)(h->h_pack + h->off_npairs);
-    for (size_t b = 0; b < B; ++b) {
-      const size_t row = b * (size_t)h->pmax * 2;
-      for (int i = 0; i < 2 * np[b]; ++i) pairs_host[row + i] = p16[row + i];
+  if (pairs_host || npairs_host || status_host || reward_host || makespan_host || done_host) {
+    const size_t stride = (size_t)a.rec_stride;
+    for (size_t b = 0; b < B; ++b) {   // unpack the records; only the valid prefix of every pair row is defined
+      const uint32_t* rec = h->h_rec + b * stride;
+      const int np = (int)L2S_REC_NPAIRS(rec[0]);
+      if (pairs_host) {
+        int32_t* row = pairs_host + b * (size_t)h->pmax * 2;
+        for (int i = 0; i < np; ++i) {
+          row[2 * i] = (int32_t)(rec[L2S_REC_HEADER_WORDS + i] & 0xffffu);
+          row[2 * i + 1] = (int32_t)(rec[L2S_REC_HEADER_WORDS + i] >> 16);
+        }
+      }
+      if (npairs_host) npairs_host[b] = np;
+      if (status_host) status_host[b] = L2S_REC_STATUS(rec[0]);
+      if (done_host) done_host[b] = (uint8_t)L2S_REC_DONE(rec[0]);
+      if (makespan_host) memcpy(makespan_host + b, rec + 1, 4);
+      if (reward_host) memcpy(reward_host + b, rec + 2, 4);
     }
   }
-  if (npairs_host) memcpy(npairs_host, h->h_pack + h->off_npairs, B * 4);
-  if (status_host) memcpy(status_host, h->h_pack + h->off_status, B * 4);
-  if (reward_host) memcpy(reward_host, h->h_pack + h->off_reward, B * 4);
-  if (makespan_host) memcpy(makespan_host, h->h_pack + h->off_ms, B * 4);
-  if (done_host) memcpy(done_host, h->h_pack + h->off_done, B);
-  // device copies requested by the caller in io (rare: the host path normally leaves these NULL)
-  if (io->npairs) CU(cudaMemcpyAsync(io->npairs, a.npairs, B * 4, cudaMemcpyDeviceToDevice, s));
-  if (io->status) CU(cudaMemcpyAsync(io->status, a.status, B * 4, cudaMemcpyDeviceToDevice, s));
   return L2S_OK;
 }
 

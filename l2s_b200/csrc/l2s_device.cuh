@@ -58,6 +58,7 @@ struct Layout {
   int e_mc;              // machine edges per instance n_m*(n_j-1)
   int off_tq, off_walk, off_crit, off_misc;
   int off_durw;          // >= 0: static node words staged in shared memory (small instances); -1: read from HBM
+  int off_rec;           // staging of the host record (4 + pmax words): overlays crit when that is large enough
   unsigned magic_nm;     // floor(2^32 / n_m) + 1: (x mod n_m) by multiply-shift for x < 2^16
   int bytes;             // per instance (step kernel)
 };
@@ -98,6 +99,7 @@ struct Inst {            // shared-memory view of one instance (32-bit shared ad
   uint32_t crit;         // uint16 [node_stride] chosen critical predecessor (networkx tie-break); 0 = S
   uint32_t durw;         // uint16 [node_stride] node words, valid iff Layout::off_durw >= 0
   uint32_t misc;         // int32 [4] parked scalars
+  uint32_t rec;          // uint32 [4 + pmax] host record staging (valid after the critical path has been traced)
 };
 
 __device__ __forceinline__ Inst inst_view(const Layout& L, uint32_t base) {
@@ -107,6 +109,7 @@ __device__ __forceinline__ Inst inst_view(const Layout& L, uint32_t base) {
   s.crit = base + L.off_crit;
   s.durw = base + (L.off_durw >= 0 ? L.off_durw : 0);
   s.misc = base + L.off_misc;
+  s.rec = base + L.off_rec;
   return s;
 }
 

@@ -283,15 +283,15 @@ struct StepArgs {
   float* reward;
   uint8_t* done;
   int32_t* pairs;
-  uint16_t* pairs16;       // packed host-path copy of the pair list: uint16 [B][pmax][2]
   int32_t* npairs;
   int32_t* status;
   int pmax;
-  // mirrors of the per-instance scalars inside the packed host-result block (l2s_step_host)
-  float* makespan2;
-  float* incumbent2;
-  float* reward2;
-  uint8_t* done2;
+  // host path (l2s_step_host): ONE record per instance, staged in shared memory and written by the whole warp as
+  // one coalesced store -- normally straight into mapped pinned host memory (see include/l2s_b200.h):
+  //   word 0: npairs | done << 16 | (status & 0xff) << 24;  words 1-3: makespan, reward, incumbent (float32);
+  //   words 4..4+npairs: the feasible pairs, a0 | a1 << 16
+  uint32_t* rec;
+  int rec_stride;          // words per record = 4 + pmax
   // test introspection (l2s_export_state): evaluate only, no mutation
   int export_only;
   int32_t* ex_est;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
       if (a.status) a.status[b] = status;
       if (a.npairs) a.npairs[b] = 0;
       if (a.done) a.done[b] = 1;
-      if (a.done2) a.done2[b] = 1;
+      if (a.rec) a.rec[(size_t)b * a.rec_stride] = 0x10000u | (0xfbu << 24);   // done, no pairs, status -5
     }
     return;
   }
@@ -448,15 +448,16 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     if (lane == 0) a.ex_path_len[b] = len;
   }
   int32_t* po = a.pairs ? a.pairs + (size_t)b * a.pmax * 2 : nullptr;
-  uint32_t* po16 = a.pairs16 ? reinterpret_cast<uint32_t*>(a.pairs16) + (size_t)b * a.pmax : nullptr;
   const int pmax = a.pmax;
+  const uint32_t stage = s.rec;
+  uint32_t* const rec = a.rec;
   int np = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
     if (idx < pmax) {
       if (po) {
         po[2 * idx] = u;
         po[2 * idx + 1] = v;
       }
-      if (po16) po16[idx] = (uint32_t)u | ((uint32_t)v << 16);
+      if (rec) sts32(stage + 16u + 4u * idx, (int)((uint32_t)u | ((uint32_t)v << 16)));
     }
   });
   if (np < 0) { status = status ? status : np; np = 0; }
@@ -481,13 +482,20 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     if (a.incumbent) a.incumbent[b] = (float)inc;
     if (a.reward) a.reward[b] = (float)reward;
     if (a.done) a.done[b] = np == 0;
-    if (a.makespan2) a.makespan2[b] = (float)ms;
-    if (a.incumbent2) a.incumbent2[b] = (float)inc;
-    if (a.reward2) a.reward2[b] = (float)reward;
-    if (a.done2) a.done2[b] = np == 0;
     if (a.npairs) a.npairs[b] = np;
     if (a.status) a.status[b] = status;
     if (status) record_error(a.st.err, status, b);
+    if (rec) {
+      sts32(stage, (int)((uint32_t)np | (np == 0 ? 0x10000u : 0u) | ((uint32_t)(status & 0xff) << 24)));
+      sts32(stage + 4u, __float_as_int((float)ms));
+      sts32(stage + 8u, __float_as_int((float)reward));
+      sts32(stage + 12u, __float_as_int((float)inc));
+    }
+  }
+  if (rec) {
+    __syncwarp();
+    uint32_t* r = rec + (size_t)b * a.rec_stride;
+    for (int i = lane; i < 4 + np; i += 32) r[i] = (uint32_t)lds32(stage + 4u * i);
   }
 }
 
@@ -567,7 +575,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
       if (a.status) a.status[b] = -5;
       if (a.npairs) a.npairs[b] = 0;
       if (a.done) a.done[b] = 1;
-      if (a.done2) a.done2[b] = 1;
+      if (a.rec) a.rec[(size_t)b * a.rec_stride] = 0x10000u | (0xfbu << 24);   // done, no pairs, status -5
     }
     return;
   }
@@ -651,15 +659,16 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     if (lane == 0) a.ex_path_len[b] = len;
   }
   int32_t* po = a.pairs ? a.pairs + (size_t)b * a.pmax * 2 : nullptr;
-  uint32_t* po16 = a.pairs16 ? reinterpret_cast<uint32_t*>(a.pairs16) + (size_t)b * a.pmax : nullptr;
   const int pmax = a.pmax;
+  const uint32_t stage = s.rec;
+  uint32_t* const rec = a.rec;
   int np = n5_moves(L, s, rp, len, tabu0, tabu1, lane, [&](int idx, int u, int v) {
     if (idx < pmax) {
       if (po) {
         po[2 * idx] = u;
         po[2 * idx + 1] = v;
       }
-      if (po16) po16[idx] = (uint32_t)u | ((uint32_t)v << 16);
+      if (rec) sts32(stage + 16u + 4u * idx, (int)((uint32_t)u | ((uint32_t)v << 16)));
     }
   });
   if (np < 0) { status = status ? status : np; np = 0; }
@@ -682,13 +691,20 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     if (a.incumbent) a.incumbent[b] = (float)inc;
     if (a.reward) a.reward[b] = (float)reward;
     if (a.done) a.done[b] = np == 0;
-    if (a.makespan2) a.makespan2[b] = (float)ms;
-    if (a.incumbent2) a.incumbent2[b] = (float)inc;
-    if (a.reward2) a.reward2[b] = (float)reward;
-    if (a.done2) a.done2[b] = np == 0;
     if (a.npairs) a.npairs[b] = np;
     if (a.status) a.status[b] = status;
     if (status) record_error(a.st.err, status, b);
+    if (rec) {
+      sts32(stage, (int)((uint32_t)np | (np == 0 ? 0x10000u : 0u) | ((uint32_t)(status & 0xff) << 24)));
+      sts32(stage + 4u, __float_as_int((float)ms));
+      sts32(stage + 8u, __float_as_int((float)reward));
+      sts32(stage + 12u, __float_as_int((float)inc));
+    }
+  }
+  if (rec) {
+    __syncwarp();
+    uint32_t* r = rec + (size_t)b * a.rec_stride;
+    for (int i = lane; i < 4 + np; i += 32) r[i] = (uint32_t)lds32(stage + 4u * i);
   }
 }
 

@@ -5,28 +5,30 @@
  * model/actor.py:216-226) and takes actions back as a list of [a0, a1] (env/environment.py:356).  At large
  * batch sizes building ~10 small lists per instance dominates a step of the drop-in, so the two conversions
  * are done here with the C API (called through ctypes.PyDLL, GIL held).  No computation happens here: the
- * inputs are the pinned host buffers that l2s_step_host filled.
+ * inputs are the pinned host records that the step kernel wrote (l2s_host_records).
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <stdint.h>
 
-/* pairs16 [B, pmax, 2] uint16, npairs [B] -> list[B] of list[P] of [a0, a1]; an instance without moves gets
- * [[0, 0]] exactly like JsspN5.feasible_actions. */
-PyObject* l2s_build_move_lists(const uint16_t* pairs16, const int32_t* npairs, int B, int pmax) {
+/* Host records of l2s_step_host ([B][stride] uint32, see include/l2s_b200.h: word 0 = npairs | ..., words 4.. =
+ * a0 | a1 << 16) -> list[B] of list[P] of [a0, a1]; an instance without moves gets [[0, 0]] exactly like
+ * JsspN5.feasible_actions. */
+PyObject* l2s_build_move_lists(const uint32_t* records, int stride, int B) {
+  const int pmax = stride - 4;
   /* ~10 container objects per instance: keep the cyclic collector from re-scanning them while they are built */
   const int gc_was_enabled = PyGC_Disable();
   PyObject* outer = PyList_New(B);
   if (!outer) { if (gc_was_enabled) PyGC_Enable(); return NULL; }
   for (int b = 0; b < B; ++b) {
-    int c = npairs[b];
+    const uint32_t* row = records + (size_t)b * stride + 4;
+    int c = (int)(row[-4] & 0xffffu);
     if (c > pmax) c = pmax;
-    const uint16_t* row = pairs16 + (size_t)b * pmax * 2;
     int m = c > 0 ? c : 1;
     PyObject* inner = PyList_New(m);
     if (!inner) { Py_DECREF(outer); if (gc_was_enabled) PyGC_Enable(); return NULL; }
     for (int i = 0; i < m; ++i) {
-      long a0 = c > 0 ? row[2 * i] : 0, a1 = c > 0 ? row[2 * i + 1] : 0;
+      long a0 = c > 0 ? (long)(row[i] & 0xffffu) : 0, a1 = c > 0 ? (long)(row[i] >> 16) : 0;
       PyObject* pair = PyList_New(2);
       PyObject* x0 = PyLong_FromLong(a0);
       PyObject* x1 = PyLong_FromLong(a1);

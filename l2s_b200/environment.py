@@ -119,15 +119,14 @@ class JsspN5:
             _capi.check(self._lib.l2s_create(self.n_job, self.n_mch, B, self.pmax, device.index, C.byref(h)),
                         "l2s_create")
             self._h, self._key, self._device = h, key, device
-            p = [_capi.c_u16p(), _capi.c_i32p(), _capi.c_i32p(), _capi.c_f32p(), _capi.c_f32p(), _capi.c_f32p(),
-                 _capi.c_u8p(), _capi.c_i32p()]
-            _capi.check(self._lib.l2s_host_buffers(h, *[C.byref(q) for q in p]), "l2s_host_buffers")
-            pm = self._lib.l2s_pmax(h)
-            self._h_pairs = _np_view(p[0], (B, pm, 2), np.uint16)
-            self._h_npairs = _np_view(p[1], (B,), np.int32)
-            self._h_status = _np_view(p[2], (B,), np.int32)
-            self._h_actions = _np_view(p[7], (B, 2), np.int32)
-            self._h_actions_ptr = C.cast(p[7], C.c_void_p)
+            rec, stride, act = _capi.c_u32p(), C.c_int(0), _capi.c_i32p()
+            _capi.check(self._lib.l2s_host_records(h, C.byref(rec), C.byref(stride), C.byref(act)),
+                        "l2s_host_records")
+            # pinned host records the step kernel writes (include/l2s_b200.h): word 0 = npairs | done << 16 |
+            # status << 24, words 4.. = a0 | a1 << 16
+            self._h_rec = _np_view(rec, (B, stride.value), np.uint32)
+            self._h_actions = _np_view(act, (B, 2), np.int32)
+            self._h_actions_ptr = C.cast(act, C.c_void_p)
             n1 = self.n_oprs + 2
             # static tensors, cached: conjunctive edges in the reference's order (env/environment.py:62-69,
             # 301) and the node->graph map (:314)
@@ -267,7 +266,7 @@ class JsspN5:
         B, device = self._key[0], self._device
         n1 = self.n_oprs + 2
         e_mc = self.n_mch * (self.n_job - 1)
-        pm = self._h_pairs.shape[1]
+        pm = self._h_rec.shape[1] - _capi.REC_HEADER_WORDS
         return dict(x=torch.empty((B * n1, 3), dtype=torch.float32, device=device),
                     emc=torch.empty((2, B * e_mc), dtype=torch.int64, device=device),
                     ms=torch.empty((B, 1), dtype=torch.float32, device=device),
@@ -363,21 +362,24 @@ class JsspN5:
             a_ptr = self._h_actions_ptr
         _capi.check(self._lib.l2s_step_host(self._h, C.byref(io), a_ptr, None, None, None, None, None, None,
                                             _stream_ptr(device)), "l2s_step")
-        status = self._h_status
-        if status.any():
+        rec = self._h_rec
+        head = rec[:, 0]
+        if (head >> 24).any():
+            status = (head >> 24).astype(np.uint8).view(np.int8)
             b = int(np.nonzero(status)[0][0])
             # drain the sticky device error word so that the next call starts clean
             self._lib.l2s_poll_error(self._h, None, _stream_ptr(device))
             _raise_status(int(status[b]), b, "step")
         self.current_objs = ms
         self.incumbent_objs = inc
-        npairs = self._h_npairs
         glue = _capi.pylists()
         if glue is not None:
-            fa = glue.l2s_build_move_lists(self._h_pairs.ctypes.data, npairs.ctypes.data, B, self._h_pairs.shape[1])
+            fa = glue.l2s_build_move_lists(rec.ctypes.data, rec.shape[1], B)
         else:
-            mask = np.arange(self._h_pairs.shape[1])[None, :] < npairs[:, None]
-            flat = self._h_pairs[mask].tolist()
+            npairs = (head & 0xffff).astype(np.int64)
+            words = rec[:, _capi.REC_HEADER_WORDS:]
+            sel = words[np.arange(words.shape[1])[None, :] < npairs[:, None]]
+            flat = np.stack([sel & 0xffff, sel >> 16], axis=1).tolist()
             ends = np.cumsum(npairs).tolist()
             fa, s = [], 0
             for e in ends:

@@ -238,7 +238,10 @@ def test_python_list_glue_matches_numpy_route():
     B, pm = 257, 12
     npairs = rng.randint(0, pm + 1, size=B).astype(np.int32)
     pairs = rng.randint(1, 4000, size=(B, pm, 2)).astype(np.uint16)
-    fa = g.l2s_build_move_lists(pairs.ctypes.data, npairs.ctypes.data, B, pm)
+    rec = np.zeros((B, 4 + pm), np.uint32)      # host records: word 0 = npairs | flags, words 4.. = a0 | a1 << 16
+    rec[:, 0] = npairs.astype(np.uint32) | (np.uint32(1) << 16) * (npairs == 0) | rng.randint(0, 2, size=B).astype(np.uint32) << 24
+    rec[:, 4:] = pairs[:, :, 0].astype(np.uint32) | (pairs[:, :, 1].astype(np.uint32) << 16)
+    fa = g.l2s_build_move_lists(rec.ctypes.data, rec.shape[1], B)
     want = [pairs[b, :npairs[b]].tolist() if npairs[b] else [[0, 0]] for b in range(B)]
     assert fa == want and all(type(p) is list and type(p[0]) is int for f in fa for p in f)
     acts = [f[len(f) // 2] for f in fa]
