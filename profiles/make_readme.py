@@ -52,7 +52,7 @@ Files: `bench_r1_1gpu.json`, `bench_r1_8gpu.json` (bench lines), `launches_r1_be
 
 * value (device-resident): **{b['value']:.3e} inst-steps/s**, {b['ms_per_step']*1e3:.1f} us per `l2s::step_kernel` launch over 8192 instances of 20x15
 * roofline: achieved {b['roofline']['achieved']:.0f} GB/s algorithmic = **{b['roofline']['frac']:.3f} of the measured HBM peak** ({b['roofline']['peak']} GB/s)
-* e2e (C-ABI `l2s_step_host`: host actions read in place from pinned memory, kernel, one packed D2H, sync per step): {b['e2e']['value']:.3e} inst-steps/s
+* e2e (C-ABI `l2s_step_host`: the kernel reads host actions from and writes per-instance result records to pinned host memory, sync per step): {b['e2e']['value']:.3e} inst-steps/s
 * e2e through the Python drop-in (`JsspN5.step`, Python lists in/out): {b['e2e_python_api']['value']:.3e} inst-steps/s
 * evaluator (`Evaluator.forward` on int64 COO): {b['evaluator']['graphs_per_s']:.3e} graphs/s = {b['evaluator']['achieved_gbs']:.0f} GB/s ({b['evaluator']['frac_of_peak']:.3f} of peak)
 * fused K-step kernel (`l2s_run`): {b['fused_run']['random_policy_inst_steps_per_s']:.3e} inst-steps/s (random policy), {b['fused_run']['greedy_policy_inst_steps_per_s']:.3e} (greedy best-neighbour)
