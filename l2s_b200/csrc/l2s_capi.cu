@@ -156,6 +156,12 @@ const char* l2s_status_string(int s) {
 
 int l2s_version(void) { return 100; }
 
+#ifdef L2S_TIMELINE
+int l2s_debug_timeline(unsigned long long* dev_buf) {
+  return cudaMemcpyToSymbol(g_timeline, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* out) {
   if (!out || n_j < 2 || n_m < 1 || batch < 1 || pmax < 0) return L2S_ERR_INVALID_ARG;
   if (pmax == 0) pmax = 32;

@@ -267,6 +267,14 @@ __device__ __forceinline__ float div_rn(float x, float c, float r, int mode) {
   return q;
 }
 
+#ifdef L2S_TIMELINE
+__device__ unsigned long long* g_timeline = nullptr;   // [B][12]: smid, globaltimer start, clock64 stamps
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TL(k) do { if (lane == 0 && g_timeline) g_timeline[(size_t)b * 12 + (k)] = (k) <= 1 ? gtimer() : (unsigned long long)clock64(); } while (0)
+#else
+#define TL(k) do {} while (0)
+#endif
+
 struct StepArgs {
   Layout L;
   State st;
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   const Inst s = inst_view(L, smem_addr(smem_step) + (uint32_t)w * (uint32_t)L.bytes);
   const int n = L.n, n1 = L.n1;
 
+  TL(0); TL(2);
   int a0 = 0, a1 = 0;
   if (a.actions && !a.export_only) {
     a0 = a.actions[2 * b];
@@ -323,7 +332,8 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   // park the scalars that are only needed at the very end in shared memory (registers are the occupancy limit)
   if (lane == 0) { sts32(s.misc, inc_in); sts32(s.misc + 4u, cur_in); }
   __syncwarp();
-  // position of a0 in the machine orders: scan the staged walk words (no index array to keep in HBM)
+  // position of a0 in the machine orders: scan the staged walk words (no index array to keep up to date in HBM;
+  // looking up a0's machine row first costs a dependent global load and measured 5 % slower)
   int i0 = -1;
   if (a0 >= 1 && a0 <= n) {
     for (int i = lane; i < n; i += 32)
@@ -331,6 +341,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     i0 = __reduce_max_sync(kFull, i0);
   }
 
+  TL(3);   // staged + searched
   int status = 0;
   // 1. N5 swap (change_nxgraph_topology :318-354) + tabu update (:370-380)
   {
@@ -353,6 +364,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     }
   }
 
+  TL(4);   // swapped
   // 2. evaluate (Evaluator.forward, env/message_passing_evl.py:161-199): forward + backward sweep
   const int ms = evaluate_instance(L, s, lane, true);
   if (ms < 0) {
@@ -366,6 +378,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     }
     return;
   }
+  TL(5);   // evaluated
   const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   // latest start of S = min over job-first ops (:195 on the S row)
   int qs = 0;
@@ -384,8 +397,24 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   if (a.x) {
     float* xo = a.x + (size_t)b * n1 * 3 + 3 * lane;
     const float fms = (float)ms;
-    if (a.div_high == 1 && a.div_fea == 1) {
-      // common case: one FMA residual correction reproduces the IEEE quotient (verified on the host)
+    if (a.div_high == 1 && a.div_fea == 1 && !(n1 & 1)) {
+      // common case (one FMA residual correction reproduces the IEEE quotient, verified on the host; even node
+      // count => 8-byte aligned rows): two adjacent nodes per lane, 64-bit shared loads, 64-bit global stores
+      const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
+      float2* xo2 = reinterpret_cast<float2*>(a.x + (size_t)b * n1 * 3) + 3 * lane;
+      for (int p = lane; p < (n1 >> 1); p += 32, xo2 += 96) {
+        const unsigned dw = (unsigned)lds32(s.durw + 4u * p);
+        const int2 f = lds64(fin + 8u * p), t = lds64(q + 8u * p);
+        const int d0 = (int)(dw & kDurMask), d1 = (int)((dw >> 16) & kDurMask);
+        const float fd0 = (float)d0, fe0 = (float)(f.x - d0), fl0 = fms - (float)t.x;
+        const float fd1 = (float)d1, fe1 = (float)(f.y - d1), fl1 = fms - (float)t.y;
+        const float q00 = __fmul_rn(fd0, rh), q01 = __fmul_rn(fe0, rf), q02 = __fmul_rn(fl0, rf);
+        const float q10 = __fmul_rn(fd1, rh), q11 = __fmul_rn(fe1, rf), q12 = __fmul_rn(fl1, rf);
+        xo2[0] = make_float2(__fmaf_rn(__fmaf_rn(-ch, q00, fd0), rh, q00), __fmaf_rn(__fmaf_rn(-cf, q01, fe0), rf, q01));
+        xo2[1] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q02, fl0), rf, q02), __fmaf_rn(__fmaf_rn(-ch, q10, fd1), rh, q10));
+        xo2[2] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q11, fe1), rf, q11), __fmaf_rn(__fmaf_rn(-cf, q12, fl1), rf, q12));
+      }
+    } else if (a.div_high == 1 && a.div_fea == 1) {
       const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
       for (int i = lane; i < n1; i += 32, xo += 96) {
         const int d = lds16(s.durw + 2u * i) & kDurMask;
@@ -413,6 +442,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     }
   }
 
+  TL(6);   // x written
   // 4. machine edges ascending by source (dag2pyg :300-305).  q is dead now: its storage holds the node-indexed
   //    machine successors (msu) and, after them, the reversed critical path.
   //    Node ids of a slice fit 32 bits (checked in l2s_create): 32-bit arithmetic, 64-bit stores.
@@ -441,12 +471,14 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   }
   __syncwarp();
 
+  TL(7);   // link + emc
   // 5. critical path (nx.dag_longest_path, :77) and N5 move set (_get_pairs :84-105)
   const int len = trace_path(L, s, ms, lane, rp);
   if (a.ex_path) {
     for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = lds16(rp + 2u * (len - 1 - i));
     if (lane == 0) a.ex_path_len[b] = len;
   }
+  TL(8);   // traced
   int32_t* po = a.pairs ? a.pairs + (size_t)b * a.pmax * 2 : nullptr;
   const int pmax = a.pmax;
   const uint32_t stage = s.rec;
@@ -463,6 +495,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   if (np < 0) { status = status ? status : np; np = 0; }
   if (np > pmax) { status = status ? status : -8; np = pmax; }
 
+  TL(9);   // moves
   // 6. reward / incumbent / current (:359-367)
   if (lane == 0) {
     const int inc_old = lds32(s.misc), cur_old = lds32(s.misc + 4u);
@@ -497,6 +530,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     uint32_t* r = rec + (size_t)b * a.rec_stride;
     for (int i = lane; i < 4 + np; i += 32) r[i] = (uint32_t)lds32(stage + 4u * i);
   }
+  TL(10); TL(1);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -525,10 +559,8 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   stage_instance(L, s, a.st, b, tid, true, nthr);
   __syncthreads();
   if (a0 >= 1 && a0 <= n) {
-    int i0 = -1;
     for (int i = tid; i < n; i += nthr)
-      if ((lds32(s.walk + 4u * i) & (int)kWId) == a0) i0 = i;
-    if (i0 >= 0) sh[0] = i0;     // a node id occurs exactly once
+      if ((lds32(s.walk + 4u * i) & (int)kWId) == a0) sh[0] = i;     // a node id occurs exactly once
   }
   __syncthreads();
   const int i0 = sh[0];
