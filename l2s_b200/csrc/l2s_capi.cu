@@ -160,6 +160,11 @@ int l2s_version(void) { return 100; }
 int l2s_debug_timeline(unsigned long long* dev_buf) {
   return cudaMemcpyToSymbol(g_timeline, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -2;
 }
+int l2s_debug_levels(unsigned long long* out2, int reset) {   // {sum of levels, sweeps} since the last reset
+  if (out2 && cudaMemcpyFromSymbol(out2, g_dbg_levels, 16) != cudaSuccess) return -2;
+  if (reset) { unsigned long long z[2] = {0, 0}; if (cudaMemcpyToSymbol(g_dbg_levels, z, 16) != cudaSuccess) return -2; }
+  return 0;
+}
 #endif
 
 int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* out) {

@@ -189,6 +189,9 @@ __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, c
 // the serial spine of the whole step.  Critical predecessors / machine successors are derived afterwards in
 // one data-parallel pass (link_pass).
 // ------------------------------------------------------------------------------------------------------
+#ifdef L2S_TIMELINE
+__device__ unsigned long long g_dbg_levels[2] = {0ull, 0ull};   // diagnostic build: sum of level trips, number of sweeps
+#endif
 __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m, int dir, bool active, int& last) {
   const int n_j = L.n_j;
   const uint32_t a_self = s.tq + (dir ? 4u * L.n1p : 0u);            // &tq[base + 0]
@@ -240,12 +243,18 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
         : "memory");
     __syncwarp();
   };
+#ifdef L2S_TIMELINE
+  const int budget0 = budget;
+#endif
   while (true) {
     level();
     level();
     if (!__any_sync(kFull, left > 0)) break;
     if (--budget < 0) { last = prevval; return false; }
   }
+#ifdef L2S_TIMELINE
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&g_dbg_levels[0], 2ull * (unsigned long long)(budget0 - budget + 1)); atomicAdd(&g_dbg_levels[1], 1ull); }
+#endif
   last = prevval;
   return true;
 }

@@ -274,6 +274,7 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #else
 #define TL(k) do {} while (0)
 #endif
+#define TLC(k) do { if (tid == 0) { const int lane = 0; TL(k); (void)lane; } } while (0)
 
 struct StepArgs {
   Layout L;
@@ -549,6 +550,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   const Inst s = inst_view(L, smem_addr(smem_step));
   const int n = L.n, n1 = L.n1;
 
+  TLC(0); TLC(2);
   int a0 = 0, a1 = 0;
   if (a.actions && !a.export_only) {
     a0 = a.actions[2 * b];
@@ -556,6 +558,18 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   }
   int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
   if (tid < 8) sh[tid] = tid == 0 ? -1 : 0;
+  // the static node words (durations by node id) are not staged for large instances: fetch this thread's share
+  // for the feature loop NOW (clamped index: no select that would wait for the data), so that the loads are in
+  // flight during staging and the sweeps instead of being a chain of dependent global-load latencies inside that
+  // loop (measured at 100x20: 9-11 us -> 1-3 us)
+  constexpr int kDurRegs = 16;
+  const uint16_t* gdurw = a.st.durw + (size_t)b * L.node_stride;
+  const bool dur_in_regs = (n1 + nthr - 1) / nthr <= kDurRegs;
+  int dreg[kDurRegs];
+  if (dur_in_regs && a.x) {
+#pragma unroll
+    for (int k = 0; k < kDurRegs; ++k) dreg[k] = (int)__ldg(gdurw + min(tid + k * nthr, n1 - 1));
+  }
   stage_instance(L, s, a.st, b, tid, true, nthr);
   __syncthreads();
   if (a0 >= 1 && a0 <= n) {
@@ -563,6 +577,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
       if ((lds32(s.walk + 4u * i) & (int)kWId) == a0) sh[0] = i;     // a node id occurs exactly once
   }
   __syncthreads();
+  TLC(3);
   const int i0 = sh[0];
   int status = 0;
   if (w == 0) {
@@ -583,7 +598,12 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     const int r = sh[1];
     if (r == 0) { tabu0 = a1; tabu1 = a0; } else if (r < 0) status = r;
   }
-  // evaluation: forward sweep on warp 0, backward sweep on warp 1 (or both on warp 0 if the CTA has one warp)
+  TLC(4);
+  // evaluation: forward sweep on warp 0, backward sweep on warp 1 (or both on warp 0 if the CTA has one warp).
+  // __syncthreads does not reconverge a warp whose lanes arrived separately (lane 0 took the write-back branch
+  // above): without the explicit __syncwarp the sweep below would run with the warp split in two, every level
+  // paying the divergent path of its own __syncwarp (measured: 255 ns instead of 64 ns per level)
+  __syncwarp();
   if (w == 0) {
     int last;
     const bool ok = wavefront(L, s, lane, 0, lane < L.n_m, last);
@@ -600,6 +620,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     if (lane == 0) sh[5] = ok2;
   }
   __syncthreads();
+  TLC(5);
   const int ms = sh[3];
   if (!sh[4] || !sh[5]) {
     if (tid == 0) {
@@ -611,7 +632,6 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     }
     return;
   }
-  const uint16_t* gdurw = a.st.durw + (size_t)b * L.node_stride;
   const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
   {
     int qs = 0;
@@ -630,12 +650,27 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   if (a.x) {
     float* xo = a.x + (size_t)b * n1 * 3;
     const float fms = (float)ms;
-    for (int i = tid; i < n1; i += nthr) {
-      const int d = __ldg(gdurw + i) & kDurMask;
-      const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
-      xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
-      xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
-      xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
+    if (dur_in_regs) {
+#pragma unroll
+      for (int k = 0; k < kDurRegs; ++k) {
+        const int i = tid + k * nthr;
+        if (i < n1) {
+          const int d = dreg[k] & kDurMask;
+          const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
+          xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
+          xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
+          xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int i = tid; i < n1; i += nthr) {
+        const int d = __ldg(gdurw + i) & kDurMask;
+        const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
+        xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
+        xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
+        xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
+      }
     }
   }
   if (a.ex_est) {
@@ -645,10 +680,12 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
       a.ex_lst[(size_t)b * n1 + i] = ms - lds32(q + 4u * i);
     }
   }
+  TLC(6);
   __syncthreads();   // q is dead from here on: its storage holds msu and then the reversed critical path
   const uint32_t msu = q, rp = q + 2u * (uint32_t)n1;
   if (a.emc) link_pass<true>(L, s, msu, tid, nthr); else link_pass<false>(L, s, msu, tid, nthr);
   __syncthreads();
+  TLC(7);
   // the edge list is written by warps 1.. while warp 0 already traces the critical path (a single-warp CTA does
   // both in turn); msu and rp are disjoint parts of the dead q half
   const int ew = nw > 1 ? nw - 1 : 1, myw = nw > 1 ? w - 1 : 0;
@@ -685,7 +722,9 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     }
   }
   if (w != 0) return;
+  __syncwarp();
   const int len = trace_path(L, s, ms, lane, rp);
+  TLC(8);
   if (a.ex_path) {
     for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = lds16(rp + 2u * (len - 1 - i));
     if (lane == 0) a.ex_path_len[b] = len;
@@ -703,6 +742,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
       if (rec) sts32(stage + 16u + 4u * idx, (int)((uint32_t)u | ((uint32_t)v << 16)));
     }
   });
+  TLC(9);
   if (np < 0) { status = status ? status : np; np = 0; }
   if (np > pmax) { status = status ? status : -8; np = pmax; }
   if (lane == 0) {
@@ -738,6 +778,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     uint32_t* r = rec + (size_t)b * a.rec_stride;
     for (int i = lane; i < 4 + np; i += 32) r[i] = (uint32_t)lds32(stage + 4u * i);
   }
+  TLC(10); TLC(1);
 }
 
 // ------------------------------------------------------------------------------------------------------

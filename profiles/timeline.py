@@ -1,6 +1,6 @@
 """Per-instance timeline of one `l2s::step_kernel` launch (20x15): when every instance starts / ends (globaltimer)
 and how long each phase takes (clock64), from a build with -DL2S_TIMELINE (lane 0 of every warp stores 11 stamps).
-Diagnostic build only -- never used for bench numbers.   usage: python profiles/timeline.py [batch]"""
+Diagnostic build only -- never used for bench numbers.   usage: python profiles/timeline.py [batch] [shape]"""
 import os, subprocess, sys, ctypes as C
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,8 +16,8 @@ from l2s_b200 import JsspN5, _capi
 from bench import gen_instances
 lib = _capi.lib()
 raw = C.CDLL(TL_LIB)
-n_j, n_m = 20, 15
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+n_j, n_m = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "20x15").split("x")]
 dev = torch.device("cuda", 0)
 env = JsspN5(n_j, n_m, 1, 99)
 env.reset(gen_instances(n_j, n_m, B, 1), "fdd-divide-mwkr", dev)
@@ -33,10 +33,15 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for k in range(30):
     if k == 29:
         assert raw.l2s_debug_timeline(C.c_void_p(tl.data_ptr())) == 0
+        torch.cuda.synchronize()
+        raw.l2s_debug_levels(None, 1)
     flush.zero_()
     env.step_device(tape[k], out=out)
 torch.cuda.synchronize()
 t = tl.cpu().numpy().astype(np.int64)
+lv = (C.c_ulonglong * 2)()
+raw.l2s_debug_levels(lv, 0)
+print("sweep levels per wavefront call: mean %.1f over %d calls" % (lv[0] / max(1, lv[1]), lv[1]))
 g0, g1 = t[:, 0], t[:, 1]
 base = g0.min()
 print("launch span us", (g1.max() - base) / 1e3)
@@ -46,7 +51,7 @@ print("end    pct 0/25/50/75/100:", np.percentile(end, [0, 25, 50, 75, 100]).rou
 dur = end - start
 first = start < 2.0
 print("instances starting in first 2us:", first.sum(), " later:", (~first).sum())
-names = ["stage+search", "swap", "evaluate", "x out", "link+emc", "trace", "moves", "scalars+rec"]
+names = ["stage+search", "swap", "evaluate", "x out", "link (+emc, warp kernel)", "trace (CTA kernel: overlaps emc)", "moves", "scalars+rec"]
 ck = t[:, 2:11].astype(np.float64)
 ph = np.diff(ck, axis=1) / 1.965e3   # us at 1965 MHz
 for grp, m in (("first wave", first), ("later", ~first)):
