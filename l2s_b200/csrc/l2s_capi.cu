@@ -209,7 +209,13 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   // few instances per SM (large graphs): give every instance a whole CTA so that the SM is not left idle
   {
     const long long per_sm = (long long)(kSmemPerSm / ((size_t)L.bytes + kSmemCtaReserve));
-    h->cta_warps = small ? 0 : (per_sm <= 4 ? 8 : 4);   // measured: 150x25 best at 8, 100x20 / 50x20 at 4, 30x20 warp-per-instance
+    // warps per instance so that the co-resident instances of an SM add up to about 32 warps (measured, after the
+    // sweeps were fixed to run converged: 50x20 B=2048 best at 2, 100x20 B=1024 at 4, 150x25 B=1024 at 8;
+    // 30x20 and smaller: warp per instance)
+    long long resident = (batch + 147) / 148;
+    if (resident > per_sm) resident = per_sm;
+    if (resident < 1) resident = 1;
+    h->cta_warps = small ? 0 : (resident >= 12 ? 2 : resident >= 5 ? 4 : 8);
     if (const char* e = getenv("L2S_CTA_WARPS")) {      // experiments: force the CTA kernel (0 keeps the choice above)
       const int v = atoi(e);
       if (v > 0) { h->cta_warps = v; }
