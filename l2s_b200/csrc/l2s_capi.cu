@@ -115,8 +115,9 @@ struct l2s_handle_s {
   long long itr;
   int warps_step, warps_run, warps_init;
   int cta_warps;   // > 0: large instances -> step_kernel_cta with this many warps per instance
-  size_t run_stride;
-  int run_off_where, run_off_plist;
+  size_t run_stride, run_stride_greedy;
+  int run_off_where, run_off_plist, run_off_walk2;
+  int warps_run_greedy;
   InitLayout IL;
   // host-driven step: pinned action staging and the per-instance result records
   int32_t* d_actions;
@@ -187,6 +188,9 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->run_off_where = L.bytes;
   h->run_off_plist = L.bytes + L.node_stride * 2;
   h->run_stride = ru((long long)h->run_off_plist + (long long)pmax * 4, 16);
+  // GREEDY with n_m <= 16 evaluates two neighbours per sweep and keeps a second copy of the walk words for that
+  h->run_off_walk2 = n_m <= 16 ? (int)h->run_stride : -1;
+  h->run_stride_greedy = n_m <= 16 ? h->run_stride + (size_t)L.walk_stride * 4 : h->run_stride;
   // initial-solution builder layout
   {
     InitLayout& I = h->IL;
@@ -204,6 +208,8 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->warps_step = pick_warps(L.bytes, 4);   // step_kernel is compiled with __launch_bounds__(128, 8)
   if (const char* e = getenv("L2S_WARPS_STEP")) { int v = atoi(e); if (v > 0 && v <= 4 && (size_t)v * L.bytes <= kSmemPerCtaMax) h->warps_step = v; }
   h->warps_run = pick_warps(h->run_stride);
+  h->warps_run_greedy = pick_warps(h->run_stride_greedy);
+  if (!h->warps_run_greedy) { h->warps_run_greedy = h->warps_run; h->run_stride_greedy = h->run_stride; h->run_off_walk2 = -1; }
   h->warps_init = pick_warps(h->IL.bytes);
   if (!h->warps_step || !h->warps_run || !h->warps_init) { free(h); return L2S_ERR_UNSUPPORTED_SHAPE; }
   // few instances per SM (large graphs): give every instance a whole CTA so that the SM is not left idle
@@ -481,9 +487,12 @@ int l2s_run(l2s_handle h, int policy, int K, const int32_t* tape, uint64_t seed,
   a.pmax = h->pmax;
   a.off_where = h->run_off_where;
   a.off_plist = h->run_off_plist;
-  a.stride = (int)h->run_stride;
-  const int W = h->warps_run;
-  run_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * h->run_stride, (cudaStream_t)stream>>>(a);
+  const bool two = policy == L2S_POLICY_GREEDY && h->run_off_walk2 >= 0;
+  const size_t stride = two ? h->run_stride_greedy : h->run_stride;
+  a.off_walk2 = two ? h->run_off_walk2 : -1;
+  a.stride = (int)stride;
+  const int W = two ? h->warps_run_greedy : h->warps_run;
+  run_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * stride, (cudaStream_t)stream>>>(a);
   CU(cudaGetLastError());
   h->itr += K;
   return L2S_OK;

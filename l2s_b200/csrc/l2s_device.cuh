@@ -192,13 +192,19 @@ __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, c
 #ifdef L2S_TIMELINE
 __device__ unsigned long long g_dbg_levels[2] = {0ull, 0ull};   // diagnostic build: sum of level trips, number of sweeps
 #endif
-__device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m, int dir, bool active, int& last) {
+// half / walk: which half of tq the lane's values live in and which copy of the walk words it reads (defaults:
+// half = dir, the instance's own walk words); the greedy policy evaluates two neighbours at once with both
+// half-warps sweeping FORWARD, each in its own tq half over its own copy of the walk words.
+__device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m, int dir, bool active, int& last,
+                                          int half = -1, uint32_t walk = 0u) {
   const int n_j = L.n_j;
-  const uint32_t a_self = s.tq + (dir ? 4u * L.n1p : 0u);            // &tq[base + 0]
+  if (half < 0) half = dir;
+  if (walk == 0u) walk = s.walk;
+  const uint32_t a_self = s.tq + (half ? 4u * L.n1p : 0u);           // &tq[base + 0]
   const uint32_t a_nb = dir ? a_self + 4u : a_self - 4u;             // &tq[base +- 1]
   const unsigned bflag = dir ? kWLast : kWFirst;
   const int stepb = dir ? -4 : 4;                                    // walk step in bytes; also a_self - a_nb
-  uint32_t a_w = s.walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 : 0));
+  uint32_t a_w = walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 : 0));
   int left = active ? n_j : 0;                                       // operations still to place
   int prevval = 0;
   unsigned w = 0, wn = 0;

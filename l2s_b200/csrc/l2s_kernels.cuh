@@ -800,6 +800,7 @@ struct RunArgs {
   int pmax;
   int off_where;   // byte offsets (within the instance's smem) of the where index (uint16 [node_stride]) ...
   int off_plist;   // ... and of the uint16 pair list [pmax][2]
+  int off_walk2;   // >= 0: second copy of the walk words (GREEDY with n_m <= 16: two neighbours per sweep)
   int stride;      // shared-memory bytes per instance (state + where + pair list)
 };
 
@@ -819,7 +820,11 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
   int inc = a.st.inc[b], cur = a.st.cur[b];
   stage_instance(L, s, a.st, b, lane, false);
   __syncwarp();
-  for (int i = lane; i < L.n; i += 32) sts16(swhere + 2u * (lds32(s.walk + 4u * i) & (int)kWId), i);
+  for (int i = lane; i < L.n; i += 32) {
+    const int wd = lds32(s.walk + 4u * i);
+    sts16(swhere + 2u * (wd & (int)kWId), i);
+    if (a.off_walk2 >= 0) sts32(base + (uint32_t)a.off_walk2 + 4u * i, wd);
+  }
   __syncwarp();
   int status = 0;
   int ms = evaluate_instance(L, s, lane, false);
@@ -852,7 +857,7 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
         } else {
           // GREEDY: evaluate every neighbour, first minimum wins (conventional_baselines...:186-197)
           int best = 0x7fffffff;
-          for (int i = 0; i < np; ++i) {
+          auto trial = [&](int i) -> int {   // makespan of neighbour i by a forward sweep over a trial swap
             const int p0 = lds16(swhere + 2u * lds16(plist + 4u * i));
             const uint32_t aw = s.walk + 4u * p0;
             const unsigned w0 = (unsigned)lds32(aw), w1 = (unsigned)lds32(aw + 4u);
@@ -866,7 +871,51 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
             const int nms = evaluate_instance(L, s, lane, false);
             if (lane == 0) { sts32(aw, (int)w0); sts32(aw + 4u, (int)w1); }
             __syncwarp();
-            if (nms >= 0 && nms < best) { best = nms; pick = i; }
+            return nms;
+          };
+          if (a.off_walk2 >= 0) {
+            // two neighbours per sweep: half-warp h evaluates neighbour i+h forward in tq half h over its own
+            // copy of the walk words (a forward sweep needs only n_m <= 16 lanes)
+            const uint32_t walk2 = base + (uint32_t)a.off_walk2;
+            const int h = lane >> 4, m = lane & 15;
+            for (int i = 0; i < np; i += 2) {
+              const bool have = i + h < np;
+              uint32_t aw = 0u;
+              unsigned w0 = 0u, w1 = 0u;
+              if (have) {
+                const int p0 = lds16(swhere + 2u * lds16(plist + 4u * (i + h)));
+                aw = (h ? walk2 : s.walk) + 4u * p0;
+                w0 = (unsigned)lds32(aw);
+                w1 = (unsigned)lds32(aw + 4u);
+              }
+              __syncwarp();
+              if (have && m == 0) {
+                sts32(aw, (int)(w1 & ~kWRowEnd));
+                sts32(aw + 4u, (int)((w0 & ~kWRowEnd) | (w1 & kWRowEnd)));
+              }
+              fill_pending(L, s, lane, true);
+              __syncwarp();
+              int last = 0;
+              const bool ok = wavefront(L, s, m, 0, have && m < L.n_m, last, h, h ? walk2 : s.walk);
+              const int msA = __reduce_max_sync(kFull, h == 0 ? last : 0);
+              const int msB = __reduce_max_sync(kFull, h == 1 ? last : 0);
+              if (have && m == 0) { sts32(aw, (int)w0); sts32(aw + 4u, (int)w1); }
+              __syncwarp();
+              if (ok) {
+                if (msA < best) { best = msA; pick = i; }
+                if (i + 1 < np && msB < best) { best = msB; pick = i + 1; }
+              } else {   // a cyclic trial (cannot happen for N5 moves): judge the two neighbours one by one
+                for (int k = i; k < min(i + 2, np); ++k) {
+                  const int nms = trial(k);
+                  if (nms >= 0 && nms < best) { best = nms; pick = k; }
+                }
+              }
+            }
+          } else {
+            for (int i = 0; i < np; ++i) {
+              const int nms = trial(i);
+              if (nms >= 0 && nms < best) { best = nms; pick = i; }
+            }
           }
         }
         a0 = lds16(plist + 4u * pick);
@@ -878,7 +927,16 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
       if (r == 0) {
         tabu0 = a1;
         tabu1 = a0;
-        if (lane == 0) { sts16(swhere + 2u * a0, i0 + 1); sts16(swhere + 2u * a1, i0); }
+        if (lane == 0) {
+          sts16(swhere + 2u * a0, i0 + 1);
+          sts16(swhere + 2u * a1, i0);
+          if (a.off_walk2 >= 0) {   // mirror the three touched words into the second copy
+            const uint32_t walk2 = base + (uint32_t)a.off_walk2;
+            sts32(walk2 + 4u * i0, lds32(s.walk + 4u * i0));
+            sts32(walk2 + 4u * (i0 + 1), lds32(s.walk + 4u * (i0 + 1)));
+            if (has_t) sts32(walk2 + 4u * (i0 + 2), lds32(s.walk + 4u * (i0 + 2)));
+          }
+        }
       } else if (r < 0) {
         status = r;
       }
