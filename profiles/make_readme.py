@@ -1,6 +1,6 @@
 """Regenerates the measured tables of profiles/README_r1.md from the artefacts brought back by gpurun:
 profiles/bench_r1_1gpu.json, profiles/bench_r1_8gpu.json, profiles/launches_r1_bench_steps40.csv and (scratch)
-gpurun_out/prof_step_r1_final.ncu-rep + gpurun_out/cs_final.csv.  Run from the repo root."""
+gpurun_out/prof_step_r1_v2.ncu-rep + gpurun_out/cs_v2.csv.  Run from the repo root."""
 import collections
 import csv
 import json
@@ -18,7 +18,7 @@ for r in rows[1:]:
     agg[r[ik]][0] += 1
     agg[r[ik]][1] += v
 tot = sum(v[1] for v in agg.values())
-raw = subprocess.run("ncu -i gpurun_out/prof_step_r1_final.ncu-rep --page raw --csv", shell=True, capture_output=True, text=True).stdout
+raw = subprocess.run("ncu -i gpurun_out/prof_step_r1_v2.ncu-rep --page raw --csv", shell=True, capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h = rr[0]
 
@@ -29,7 +29,7 @@ def m(name):
 
 
 N = float(m('smsp__inst_executed.sum')[0])
-phase = subprocess.run("python profiles/by_phase.py gpurun_out/cs_final.csv %d 8192" % int(N), shell=True, capture_output=True, text=True).stdout
+phase = subprocess.run("python profiles/by_phase.py gpurun_out/cs_v2.csv %d 8192" % int(N), shell=True, capture_output=True, text=True).stdout
 traffic = (float(m('dram__bytes_read.sum')[0]) + float(m('dram__bytes_write.sum')[0])) * 1e6
 json.dump({"20x15_b8192": traffic,
            "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of l2s::step_kernel from the final ncu --set full "
