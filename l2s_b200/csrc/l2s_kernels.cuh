@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
   const int inc_in = a.st.inc[b], cur_in = a.st.cur[b];
   stage_instance(L, s, a.st, b, lane, true);
+  TL(11);   // staged
   // park the scalars that are only needed at the very end in shared memory (registers are the occupancy limit)
   if (lane == 0) { sts32(s.misc, inc_in); sts32(s.misc + 4u, cur_in); }
   __syncwarp();

@@ -52,9 +52,12 @@ dur = end - start
 first = start < 2.0
 print("instances starting in first 2us:", first.sum(), " later:", (~first).sum())
 names = ["stage+search", "swap", "evaluate", "x out", "link (+emc, warp kernel)", "trace (CTA kernel: overlaps emc)", "moves", "scalars+rec"]
+staged = (t[:, 11] - t[:, 2]) / 1.965e3   # warp kernel only: TMA staging complete (part of stage+search)
 ck = t[:, 2:11].astype(np.float64)
 ph = np.diff(ck, axis=1) / 1.965e3   # us at 1965 MHz
 for grp, m in (("first wave", first), ("later", ~first)):
+    if m.any() and (t[m, 11] > 0).all():
+        print(grp, "of which staging wait (TMA complete) %.2f us" % staged[m].mean())
     print(grp, "latency us mean %.2f" % dur[m].mean(), " phases:", " | ".join("%s %.2f" % (n, v) for n, v in zip(names, ph[m].mean(axis=0))))
 # histogram of active instances over time
 ts = np.arange(0, end.max(), 2.0)
