@@ -312,15 +312,22 @@ def run_ours(args, rank, world, local_rank):
     # host results are read in place from the handle's pinned records (l2s_host_records): zero extra copies
     sink = 0
 
-    def capi_step(r, acts):
+    # one l2s_step_io per environment, filled once (the device output pointers do not change between steps)
+    host_ios = []
+    for r in range(REPLICAS):
         o = outs[r]
-        io = _capi.StepIO(actions=None, high=99.0, fea_norm_const=1000.0, reward_type=0, is_reset=0,
-                          x=o["x"].data_ptr(), edge_index_mc=o["emc"].data_ptr(), makespan=o["ms"].data_ptr(),
-                          incumbent=o["inc"].data_ptr(), reward=o["rew"].data_ptr(), done=o["done"].data_ptr(),
-                          pairs=None, npairs=None, status=None)
-        _capi.check(lib.l2s_step_host(envs[r]._h, C.byref(io), acts.ctypes.data, None, None, None, None, None,
-                                      None, sp), "l2s_step_host")
-        return int(envs[r]._h_rec[0, 0]) + int(envs[r]._h_rec[-1, 0])     # touch the host results
+        host_ios.append(_capi.StepIO(actions=None, high=99.0, fea_norm_const=1000.0, reward_type=0, is_reset=0,
+                                     x=o["x"].data_ptr(), edge_index_mc=o["emc"].data_ptr(), makespan=o["ms"].data_ptr(),
+                                     incumbent=o["inc"].data_ptr(), reward=o["rew"].data_ptr(), done=o["done"].data_ptr(),
+                                     pairs=None, npairs=None, status=None))
+    step_host = lib.l2s_step_host
+
+    def capi_step(r, acts):
+        st = step_host(envs[r]._h, C.byref(host_ios[r]), acts.ctypes.data, None, None, None, None, None, None, sp)
+        if st < 0:
+            _capi.check(st, "l2s_step_host")
+        rec = envs[r]._h_rec
+        return int(rec[0, 0]) + int(rec[-1, 0])     # touch the host results (first and last record)
 
     for r, acts in hb[:w_e2e]:
         capi_step(r, acts)
