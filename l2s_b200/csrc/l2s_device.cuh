@@ -98,6 +98,13 @@ __device__ __forceinline__ void sts16(uint32_t a, int v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
 
+__device__ __forceinline__ int lds8(uint32_t a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return (int)v;
+}
+__device__ __forceinline__ void sts8(uint32_t a, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 struct Inst {            // shared-memory view of one instance (32-bit shared addresses)
   uint32_t tq;           // int32 [2][n1p]: [v] = est[v]+dur[v] ("fin"), [n1p+v] = tail q[v]; -1 = pending
   uint32_t walk;         // uint32 [walk_stride]

@@ -1118,6 +1118,7 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   const uint32_t succ = base + a.off_succ, heads = base + a.off_heads;   // uint16 [node_stride], uint16 [32]
   const uint32_t durw = base + a.off_durw;                               // uint16 [node_stride] node words
   const int n = L.n, n1 = L.n1, n_m = L.n_m, n_j = L.n_j;
+  TL(0); TL(2);
   if (b == 0 && lane == 0 && *a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
 
   // stage: machine successors and the "pending" sentinels by TMA bulk copies (one lane), durations -> node words
@@ -1133,35 +1134,54 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   {
     int pos = lane == 0 ? n_m - 1 : (lane - 1) % n_m;   // (i-1) mod n_m, advanced by 32 per trip
     const int step = 32 % n_m;
-    for (int i = lane; i < n1; i += 32) {
-      long long d = a.dur_i64 ? reinterpret_cast<const long long*>(a.duration)[b * n1 + i]
-                              : (long long)reinterpret_cast<const int32_t*>(a.duration)[b * n1 + i];
-      if (d < 0 || d > kDurMax) { bad = 1; d = 0; }
-      int word = (int)d;
-      if (i >= 1 && i <= n) word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
-      else if (d != 0) bad = 1;
-      sts16(durw + 2u * i, word);
-      pos += step;
-      if (pos >= n_m) pos -= n_m;
+    // all loads of a group of kDurTrips trips are issued before the first shared-memory store (which is an asm
+    // with a memory clobber and would otherwise serialise the trips into a chain of global-load latencies)
+    constexpr int kDurTrips = 6;
+    for (int i0 = lane; i0 < n1; i0 += 32 * kDurTrips) {
+      long long dv[kDurTrips];
+#pragma unroll
+      for (int k = 0; k < kDurTrips; ++k) {
+        const int i = min(i0 + 32 * k, n1 - 1);
+        dv[k] = a.dur_i64 ? reinterpret_cast<const long long*>(a.duration)[b * n1 + i]
+                          : (long long)reinterpret_cast<const int32_t*>(a.duration)[b * n1 + i];
+      }
+#pragma unroll
+      for (int k = 0; k < kDurTrips; ++k) {
+        const int i = i0 + 32 * k;
+        if (i < n1) {
+          long long d = dv[k];
+          if (d < 0 || d > kDurMax) { bad = 1; d = 0; }
+          int word = (int)d;
+          if (i >= 1 && i <= n) word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
+          else if (d != 0) bad = 1;
+          sts16(durw + 2u * i, word);
+          pos += step;
+          if (pos >= n_m) pos -= n_m;
+        }
+      }
     }
   }
   __syncwarp();
+  TL(3);   // durations converted
   mbar_wait(bar, 0);
-  // heads = operations nobody points to.  Mark successors in tq's (still unused) backward half as a bitmap.
-  const uint32_t bits = s.tq + 4u * L.n1p;          // reuse: n1 bits <= 4*n1p bytes
-  for (int i = lane; i < (n1 + 31) / 32; i += 32) sts32(bits + 4u * i, 0);
+  TL(4);   // staged
+  // heads = operations nobody points to.  One flag BYTE per node in tq's (still unused) backward half: plain
+  // stores, no atomics (a bitmap needed shared-memory atomics on a handful of words: ~10-way serialised)
+  const uint32_t flags = s.tq + 4u * L.n1p;          // n1 bytes <= 4*n1p bytes
+  const int nflag16 = (n1 + 15) >> 4;
+  for (int i = lane; i < nflag16; i += 32) sts128(flags + 16u * i, make_uint4(0u, 0u, 0u, 0u));
   __syncwarp();
   int narc = 0;
   for (int v = 1 + lane; v <= n; v += 32) {
     const int sc = lds16(succ + 2u * v);
-    if (sc) { atomicOr(reinterpret_cast<unsigned*>(smem_coo + (bits - smem_addr(smem_coo))) + (sc >> 5), 1u << (sc & 31)); ++narc; }
+    if (sc) { sts8(flags + (uint32_t)sc, 1); ++narc; }
   }
   narc = __reduce_add_sync(kFull, narc);
   __syncwarp();
   int nh = 0;
   for (int v0 = 1; v0 <= n; v0 += 32) {
     const int v = v0 + lane;
-    const bool ish = v <= n && !((lds32(bits + 4u * (v >> 5)) >> (v & 31)) & 1);
+    const bool ish = v <= n && lds8(flags + (uint32_t)v) == 0;
     const unsigned bh = __ballot_sync(kFull, ish);
     const int ph = nh + __popc(bh & ((1u << lane) - 1u));
     if (ish && ph < 32) sts16(heads + 2u * ph, v);
@@ -1174,6 +1194,7 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
     if (lane == 0) atomicCAS(a.ws.flag, 0, bad ? -6 : -5);
     return;
   }
+  TL(5);   // heads found
   // follow chain `lane` from its head into walk row `lane` (pointer chase, n_j steps)
   int chain_ok = 1;
   if (lane < n_m) {
@@ -1187,9 +1208,12 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
     if (v != 0) chain_ok = 0;      // longer than n_j (or a cycle)
   }
   chain_ok = __reduce_and_sync(kFull, chain_ok);
-  for (int i = lane; i < (n1 + 31) / 32; i += 32) sts32(bits + 4u * i, -1);   // the bitmap lived in the backward half
+  for (int i = lane; i < nflag16; i += 32)   // the flags lived in the backward half: back to "pending"
+    sts128(flags + 16u * i, make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu));
   __syncwarp();
+  TL(6);   // walk rows built
   const int ms = chain_ok ? evaluate_instance(L, s, lane, true) : -1;
+  TL(7);   // swept
   if (ms < 0) {
     if (lane == 0) atomicCAS(a.ws.flag, 0, -5);
     return;
@@ -1213,6 +1237,7 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
     lo[i] = (float)(ms - lds32(q + 4u * i));
   }
   if (lane == 0) a.ms[b] = (float)ms;
+  TL(8); TL(1);
 }
 
 }  // namespace l2s
