@@ -189,8 +189,9 @@ def test_randomised_shapes_and_durations_against_c_oracle():
     every output compared to the plain-C oracle at every step (bit-exact x, edges, pairs, rewards, incumbents)."""
     from l2s_b200 import JsspN5
     from oracle import c_oracle as CO
-    rng = np.random.RandomState(2024)
-    for case in range(24):
+    # L2S_FUZZ_SEED / L2S_FUZZ_CASES: longer one-off campaigns (e.g. 300 cases, also with L2S_CTA_WARPS forced)
+    rng = np.random.RandomState(int(os.environ.get("L2S_FUZZ_SEED", "2024")))
+    for case in range(int(os.environ.get("L2S_FUZZ_CASES", "24"))):
         n_j, n_m = int(rng.randint(3, 28)), int(rng.randint(2, 24))
         hi = int(rng.choice([3, 5, 20, 99, 400]))
         B, K = int(rng.randint(3, 40)), int(rng.randint(5, 30))
