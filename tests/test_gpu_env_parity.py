@@ -260,3 +260,24 @@ def test_plain_c_host_through_the_c_abi(tmp_path):
         assert g[8:10] == [0 if f == [[0, 0]] else len(f) for f in fa]
     x1 = [float(v) for v in lines[-2].split("=")[1].split()]
     assert np.allclose(x1, state[0][1].cpu().numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("records,zerocopy", [("0", "1"), ("1", "0"), ("0", "0")])
+def test_staged_host_paths_match_the_zero_copy_default(records, zerocopy, monkeypatch):
+    """L2S_HOST_RECORDS=0 (records via device memory + one bulk D2H) and L2S_HOST_ZEROCOPY=0 (actions via an H2D
+    copy) give the same trajectory as the default path where the kernel reads / writes pinned host memory itself."""
+    from l2s_b200 import JsspN5
+    g = np.load(os.path.join(GOLDEN, "traj_20x15_ties.npz"))
+    n_j, n_m, high, fea = [int(v) for v in g["meta"]]
+    pmax = g["pairs"].shape[2]
+    monkeypatch.setenv("L2S_HOST_RECORDS", records)
+    monkeypatch.setenv("L2S_HOST_ZEROCOPY", zerocopy)
+    env = JsspN5(n_j, n_m, 1, high, reward_type=str(g["reward_type"]), fea_norm_const=fea)   # reads the env at create
+    state, fa, done = env.reset(g["instances"], str(g["init_type"]), "cuda", init_solutions=g["mseq0"])
+    for k in range(g["tape"].shape[1]):
+        state, reward, fa, done = env.step(g["tape"][:, k].tolist(), "cuda")
+        p, c = _pairs_from_fa(fa, pmax)
+        assert np.array_equal(c, g["npairs"][k + 1]) and np.array_equal(p, g["pairs"][k + 1])
+        assert np.array_equal(reward.cpu().numpy().reshape(-1), g["reward"][k])
+        assert np.array_equal(done.cpu().numpy().reshape(-1), g["done"][k + 1])
+        assert np.array_equal(env.incumbent_objs.cpu().numpy().reshape(-1), g["incumbent"][k + 1])
