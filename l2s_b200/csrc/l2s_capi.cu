@@ -45,7 +45,7 @@ Layout make_layout(int n_j, int n_m, bool stage_durw = false, int pmax = 0) {
   L.off_tq = off;   off += 2 * L.n1p * 4;
   L.off_walk = off; off += L.walk_stride * 4;
   L.off_crit = off; off += L.node_stride * 2;
-  L.off_misc = off; off += 16;
+  L.off_misc = off; off += 32;   // parked scalars (8 B) + two mbarriers
   // small instances (warp-per-instance step kernel) keep the static node words in shared memory too (cheaper
   // feature loop); large ones (CTA-per-instance kernel) read them from HBM so that one more instance fits an SM
   L.off_durw = -1;

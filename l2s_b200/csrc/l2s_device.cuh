@@ -171,21 +171,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // (L2 resident).  Every lane then waits on the barrier (phase 0; each instance slot is used once per kernel).
 __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, const State& st, int b, int lane,
                                                bool fill_q, int nthr = 32) {
-  const uint32_t bar = s.misc + 8u;
+  const uint32_t bar = s.misc + 8u, bar2 = s.misc + 16u;
   if (lane == 0) {
     const uint32_t wbytes = (uint32_t)L.walk_stride * 4u, dbytes = L.off_durw >= 0 ? (uint32_t)L.node_stride * 2u : 0u;
     // warp-per-instance: the "pending" sentinels come from a -1 page in L2 too; a whole CTA fills them itself
     const uint32_t tbytes = nthr > 32 ? 0u : (fill_q ? 2u : 1u) * (uint32_t)L.n1p * 4u;
+    // two barriers: the walk words gate the start (action lookup, swap); the sentinels and the node words are only
+    // needed from the evaluation on (stage_wait_rest) and land while the swap is being applied
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, wbytes + dbytes + tbytes);
+    mbar_init(bar2, 1);
+    mbar_expect_tx(bar, wbytes);
     bulk_g2s(s.walk, st.walk + (size_t)b * L.walk_stride, wbytes, bar);
-    if (dbytes) bulk_g2s(s.durw, st.durw + (size_t)b * L.node_stride, dbytes, bar);
-    if (tbytes) bulk_g2s(s.tq, st.pending_page, tbytes, bar);
+    mbar_expect_tx(bar2, dbytes + tbytes);
+    if (tbytes) bulk_g2s(s.tq, st.pending_page, tbytes, bar2);
+    if (dbytes) bulk_g2s(s.durw, st.durw + (size_t)b * L.node_stride, dbytes, bar2);
   }
   if (nthr > 32) fill_pending(L, s, lane, fill_q, nthr);
-  if (nthr > 32) __syncthreads(); else __syncwarp();   // the barrier word is initialised before anyone polls it
+  if (nthr > 32) __syncthreads(); else __syncwarp();   // the barrier words are initialised before anyone polls them
   mbar_wait(bar, 0);
 }
+// second half of the staging: sentinels + node words have landed
+__device__ __forceinline__ void stage_wait_rest(const Inst& s) { mbar_wait(s.misc + 16u, 0); }
 
 // ------------------------------------------------------------------------------------------------------
 // Level-synchronous wavefront.  Lane role: machine row `m`, direction dir (0: forward est/fin from the head

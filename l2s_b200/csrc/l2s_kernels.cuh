@@ -331,8 +331,6 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   const int inc_in = a.st.inc[b], cur_in = a.st.cur[b];
   stage_instance(L, s, a.st, b, lane, true);
   TL(11);   // staged
-  // park the scalars that are only needed at the very end in shared memory (registers are the occupancy limit)
-  if (lane == 0) { sts32(s.misc, inc_in); sts32(s.misc + 4u, cur_in); }
   __syncwarp();
   // position of a0 in the machine orders: scan the staged walk words (no index array to keep up to date in HBM;
   // looking up a0's machine row first costs a dependent global load and measured 5 % slower)
@@ -367,6 +365,10 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   }
 
   TL(4);   // swapped
+  // park the scalars that are only needed at the very end in shared memory (registers are the occupancy limit);
+  // not earlier, so that their global loads do not gate the action lookup and the swap
+  if (lane == 0) { sts32(s.misc, inc_in); sts32(s.misc + 4u, cur_in); }
+  stage_wait_rest(s);
   // 2. evaluate (Evaluator.forward, env/message_passing_evl.py:161-199): forward + backward sweep
   const int ms = evaluate_instance(L, s, lane, true);
   if (ms < 0) {
@@ -600,6 +602,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     if (r == 0) { tabu0 = a1; tabu1 = a0; } else if (r < 0) status = r;
   }
   TLC(4);
+  stage_wait_rest(s);
   // evaluation: forward sweep on warp 0, backward sweep on warp 1 (or both on warp 0 if the CTA has one warp).
   // __syncthreads does not reconverge a warp whose lanes arrived separately (lane 0 took the write-back branch
   // above): without the explicit __syncwarp the sweep below would run with the warp split in two, every level
@@ -826,6 +829,7 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
     sts16(swhere + 2u * (wd & (int)kWId), i);
     if (a.off_walk2 >= 0) sts32(base + (uint32_t)a.off_walk2 + 4u * i, wd);
   }
+  stage_wait_rest(s);
   __syncwarp();
   int status = 0;
   int ms = evaluate_instance(L, s, lane, false);
