@@ -566,6 +566,8 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   a.B = batch;
   a.duration = duration;
   a.dur_i64 = duration_is_i64;
+  a.dur_tma = duration_is_i64 && ((n + 2) % 2 == 0) && (((unsigned long long)duration & 15ull) == 0);
+  if (const char* e = getenv("L2S_EVAL_DUR_TMA")) a.dur_tma = a.dur_tma && atoi(e) != 0;   // experiments
   const size_t links = (size_t)batch * L.node_stride * 2;
   a.ws.msucc = (uint16_t*)workspace;
   a.ws.conj_count = (unsigned long long*)((char*)workspace + links);

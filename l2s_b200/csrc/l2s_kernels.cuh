@@ -1102,6 +1102,7 @@ struct CooEvalArgs {
   long long B;
   const void* duration;
   int dur_i64;
+  int dur_tma;         // int64 rows 16-byte aligned: the raw durations are bulk-copied into tq and converted from there
   CooWs ws;
   float* est;
   float* lst;
@@ -1125,19 +1126,37 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   TL(0); TL(2);
   if (b == 0 && lane == 0 && *a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
 
-  // stage: machine successors and the "pending" sentinels by TMA bulk copies (one lane), durations -> node words
-  const uint32_t bar = base + a.off_bar;
+  // stage: machine successors (and, for the plain path, the "pending" sentinels) by TMA bulk copies issued by one
+  // lane.  Durations: when the int64 rows are 16-byte aligned they are bulk-copied RAW into tq (8*n1 <= 8*n1p bytes)
+  // on a second barrier and converted after the chain heads have been found, so that the largest input of the call
+  // is in flight while the warp works; otherwise they are loaded and converted here.
+  const uint32_t bar = base + a.off_bar, bar2 = bar + 8u;
   if (lane == 0) {
     const uint32_t sbytes = (uint32_t)L.node_stride * 2u, tbytes = 2u * (uint32_t)L.n1p * 4u;
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, sbytes + tbytes);
+    mbar_init(bar2, 1);
+    mbar_expect_tx(bar, sbytes + (a.dur_tma ? 0u : tbytes));
     bulk_g2s(succ, a.ws.msucc + b * L.node_stride, sbytes, bar);
-    bulk_g2s(s.tq, a.ws.pending_page, tbytes, bar);
+    if (a.dur_tma) {
+      mbar_expect_tx(bar2, (uint32_t)n1 * 8u);
+      bulk_g2s(s.tq, reinterpret_cast<const long long*>(a.duration) + b * n1, (uint32_t)n1 * 8u, bar2);
+    } else {
+      bulk_g2s(s.tq, a.ws.pending_page, tbytes, bar);
+    }
   }
   int bad = 0;
-  {
-    int pos = lane == 0 ? n_m - 1 : (lane - 1) % n_m;   // (i-1) mod n_m, advanced by 32 per trip
-    const int step = 32 % n_m;
+  // node word of node i from its duration d; pos = (i-1) mod n_m
+  auto node_word = [&](int i, long long d, int pos) -> int {
+    if (d < 0 || d > kDurMax) { bad = 1; d = 0; }
+    int word = (int)d;
+    if (i >= 1 && i <= n) word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
+    else if (d != 0) bad = 1;
+    return word;
+  };
+  const int pos0 = lane == 0 ? n_m - 1 : (lane - 1) % n_m;   // (i-1) mod n_m for i = lane, advanced by 32 per trip
+  const int step = 32 % n_m;
+  if (!a.dur_tma) {
+    int pos = pos0;
     // all loads of a group of kDurTrips trips are issued before the first shared-memory store (which is an asm
     // with a memory clobber and would otherwise serialise the trips into a chain of global-load latencies)
     constexpr int kDurTrips = 6;
@@ -1153,12 +1172,7 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
       for (int k = 0; k < kDurTrips; ++k) {
         const int i = i0 + 32 * k;
         if (i < n1) {
-          long long d = dv[k];
-          if (d < 0 || d > kDurMax) { bad = 1; d = 0; }
-          int word = (int)d;
-          if (i >= 1 && i <= n) word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
-          else if (d != 0) bad = 1;
-          sts16(durw + 2u * i, word);
+          sts16(durw + 2u * i, node_word(i, dv[k], pos));
           pos += step;
           if (pos >= n_m) pos -= n_m;
         }
@@ -1166,12 +1180,12 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
     }
   }
   __syncwarp();
-  TL(3);   // durations converted
+  TL(3);   // durations converted (plain path)
   mbar_wait(bar, 0);
   TL(4);   // staged
-  // heads = operations nobody points to.  One flag BYTE per node in tq's (still unused) backward half: plain
-  // stores, no atomics (a bitmap needed shared-memory atomics on a handful of words: ~10-way serialised)
-  const uint32_t flags = s.tq + 4u * L.n1p;          // n1 bytes <= 4*n1p bytes
+  // heads = operations nobody points to.  One flag BYTE per node in the (still unused) walk words: plain stores, no
+  // atomics (a bitmap needed shared-memory atomics on a handful of words: ~10-way serialised)
+  const uint32_t flags = s.walk;                      // n1 bytes <= 4*walk_stride bytes
   const int nflag16 = (n1 + 15) >> 4;
   for (int i = lane; i < nflag16; i += 32) sts128(flags + 16u * i, make_uint4(0u, 0u, 0u, 0u));
   __syncwarp();
@@ -1190,6 +1204,19 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
     const int ph = nh + __popc(bh & ((1u << lane) - 1u));
     if (ish && ph < 32) sts16(heads + 2u * ph, v);
     nh += __popc(bh);
+  }
+  if (a.dur_tma) {   // the raw durations have landed in tq by now: convert, then turn tq into "pending" sentinels
+    mbar_wait(bar2, 0);
+    int pos = pos0;
+    for (int i = lane; i < n1; i += 32) {
+      const int2 dd = lds64(s.tq + 8u * i);
+      const long long d = (long long)(((unsigned long long)(unsigned)dd.y << 32) | (unsigned)dd.x);
+      sts16(durw + 2u * i, node_word(i, d, pos));
+      pos += step;
+      if (pos >= n_m) pos -= n_m;
+    }
+    __syncwarp();
+    fill_pending(L, s, lane, true);
   }
   __syncwarp();
   bad = __reduce_or_sync(kFull, bad);
@@ -1212,8 +1239,6 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
     if (v != 0) chain_ok = 0;      // longer than n_j (or a cycle)
   }
   chain_ok = __reduce_and_sync(kFull, chain_ok);
-  for (int i = lane; i < nflag16; i += 32)   // the flags lived in the backward half: back to "pending"
-    sts128(flags + 16u * i, make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu));
   __syncwarp();
   TL(6);   // walk rows built
   const int ms = chain_ok ? evaluate_instance(L, s, lane, true) : -1;
