@@ -1014,34 +1014,27 @@ __device__ __forceinline__ unsigned fast_div(unsigned x, unsigned magic, unsigne
 }
 
 // classify one edge (u -> v): returns 1 for a conjunctive arc, 0 after scattering a machine arc, -1 if malformed.
-// Kept short on purpose (the ingest kernel is instruction-bound otherwise): 32-bit arithmetic (the host guarantees
-// batch*(n+2) < 2^31), one multiply-shift division to find the graph, a second one only for edges that look like
-// job arcs (v == u+1) or touch S / T.
+// Branch-free on purpose (the ingest kernel is instruction-bound and a warp sees a mix of arc kinds): 32-bit
+// arithmetic (the host guarantees batch*(n+2) < 2^31), one multiply-shift division to find the graph and one exact
+// multiply-shift remainder (operand < 2^16) for "first / last operation of a job".
+//   machine arc  : op -> op, unless the ids are consecutive inside one job
+//   conjunctive  : S -> first op of a job | last op of a job -> T | op -> next op of the same job
 __device__ __forceinline__ int coo_edge(const CooIngestArgs& a, long long u64, long long v64) {
   const unsigned n = (unsigned)a.n, n1 = (unsigned)a.n1, n_m = (unsigned)a.n_m;
-  if ((unsigned long long)(u64 | v64) >> 31) return -1;                // negative or >= 2^31
   const unsigned u = (unsigned)u64, v = (unsigned)v64;
-  if (u >= a.lim || v >= a.lim) return -1;
+  const bool small = (((unsigned long long)(u64 | v64)) >> 31) == 0ull;     // neither negative nor >= 2^31
   const unsigned bu = fast_div(u, a.magic_n1, n1);
   const unsigned base = bu * n1;
-  const unsigned ul = u - base, vl = v - base;                         // vl wraps around if v is in an earlier graph
-  if (vl >= n1) return -1;                                             // different graph
-  if (ul - 1u < n && vl - 1u < n && vl != ul + 1u) {                   // op -> op, not consecutive: machine arc
-    a.ws.msucc[bu * (unsigned)a.node_stride + ul] = (uint16_t)vl;
-    return 0;
-  }
-  if (ul == 0u) {                                                      // S -> first operation of a job
-    if (vl - 1u >= n) return -1;
-    const unsigned x = vl - 1u;
-    return x == fast_div(x, a.magic_nm, n_m) * n_m ? 1 : -1;
-  }
-  if (ul > n || vl == 0u) return -1;                                   // out of T / into S
-  // here vl == ul+1 (job arc unless u is the last of its job, then u+1 starts another job: machine arc), or v == T
-  const unsigned pos_u = (ul - 1u) - fast_div(ul - 1u, a.magic_nm, n_m) * n_m;
-  if (vl == n + 1u) return pos_u == n_m - 1u ? 1 : -1;                 // last operation of a job -> T
-  if (pos_u != n_m - 1u) return 1;                                     // job arc
-  a.ws.msucc[bu * (unsigned)a.node_stride + ul] = (uint16_t)vl;        // machine arc between consecutive node ids
-  return 0;
+  const unsigned ul = u - base, vl = v - base;                               // vl wraps around if v is in an earlier graph
+  const bool inrange = small & (u < a.lim) & (vl < n1);                      // same graph (implies v < lim)
+  const bool uop = (ul - 1u) < n, vop = (vl - 1u) < n;
+  const bool consec = vl == ul + 1u;
+  const unsigned x = ul == 0u ? vl - 1u : ul;                                // S -> v: is v first?   u -> .: is u last?
+  const bool divis = x == __umulhi(x, a.magic_nm) * n_m;                     // exact for x < 2^16
+  const bool machine = uop & vop & !(consec & !divis);
+  const bool conj = ((ul == 0u) & vop & divis) | (uop & (vl == n + 1u) & divis) | (uop & vop & consec & !divis);
+  if (inrange & machine) a.ws.msucc[bu * (unsigned)a.node_stride + ul] = (uint16_t)vl;
+  return inrange & (machine | conj) ? (machine ? 0 : 1) : -1;
 }
 
 // Each thread takes kIngestTrips x 2 edges as 16-byte loads from both rows of the [2,E] list, all issued before the
