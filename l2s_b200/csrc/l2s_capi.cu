@@ -423,9 +423,19 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
   // the PCIe traffic overlaps the launch.  (L2S_HOST_ZEROCOPY=0 / L2S_HOST_RECORDS=0 stage through device
   // memory with explicit copies instead.)
   if (actions_host) {
-    if (actions_host != h->h_actions) memcpy(h->h_actions, actions_host, B * 8);
+    const int32_t* in_place = nullptr;   // device-visible address of the caller's buffer, if it is pinned host memory
+    if (actions_host == h->h_actions) {
+      in_place = h->h_actions_dev;
+    } else if (h->zero_copy) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, actions_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+        in_place = (const int32_t*)at.devicePointer;
+      else
+        cudaGetLastError();
+    }
+    if (!in_place || !h->zero_copy) memcpy(h->h_actions, actions_host, B * 8);   // pageable caller memory: stage it
     if (h->zero_copy) {
-      a.actions = h->h_actions_dev;
+      a.actions = in_place ? in_place : h->h_actions_dev;
     } else {
       CU(cudaMemcpyAsync(h->d_actions, h->h_actions, B * 8, cudaMemcpyHostToDevice, s));
       a.actions = h->d_actions;

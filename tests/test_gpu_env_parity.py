@@ -281,3 +281,40 @@ def test_staged_host_paths_match_the_zero_copy_default(records, zerocopy, monkey
         assert np.array_equal(reward.cpu().numpy().reshape(-1), g["reward"][k])
         assert np.array_equal(done.cpu().numpy().reshape(-1), g["done"][k + 1])
         assert np.array_equal(env.incumbent_objs.cpu().numpy().reshape(-1), g["incumbent"][k + 1])
+
+
+def test_step_host_reads_pinned_caller_memory_in_place():
+    """l2s_step_host with the actions in the caller's own pinned host memory (read in place by the kernel) gives the
+    same records as with pageable memory (staged through the handle's pinned buffer)."""
+    import ctypes as C
+    from l2s_b200 import JsspN5, _capi
+    g = np.load(os.path.join(GOLDEN, "traj_10x10.npz"))
+    n_j, n_m, high, fea = [int(v) for v in g["meta"]]
+    lib = _capi.lib()
+    recs = []
+    for pinned in (True, False):
+        env = JsspN5(n_j, n_m, 1, high, reward_type=str(g["reward_type"]), fea_norm_const=fea)
+        state, fa, done = env.reset(g["instances"], str(g["init_type"]), "cuda", init_solutions=g["mseq0"])
+        B = g["instances"].shape[0]
+        x = torch.empty_like(state[0])
+        emc = torch.empty_like(state[2])
+        io = _capi.StepIO(actions=None, high=float(high), fea_norm_const=float(fea),
+                          reward_type=_capi.REWARD[str(g["reward_type"])], is_reset=0, x=x.data_ptr(),
+                          edge_index_mc=emc.data_ptr(), makespan=None, incumbent=None, reward=None, done=None,
+                          pairs=None, npairs=None, status=None)
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        out = []
+        for k in range(g["tape"].shape[1]):
+            acts = np.ascontiguousarray(g["tape"][:, k]).astype(np.int32)
+            keep = torch.from_numpy(acts).pin_memory() if pinned else None
+            ptr = keep.data_ptr() if pinned else acts.ctypes.data
+            _capi.check(lib.l2s_step_host(env._h, C.byref(io), ptr, None, None, None, None, None, None, sp), "step")
+            rec = env._h_rec.copy()
+            npairs = rec[:, 0] & 0xffff
+            rec[:, 4:][np.arange(rec.shape[1] - 4)[None, :] >= npairs[:, None]] = 0     # stale words beyond npairs
+            out.append((rec, x.cpu().numpy().copy()))
+            assert np.array_equal(npairs, g["npairs"][k + 1])
+            assert np.array_equal(rec[:, 1].view(np.float32).astype(np.int32), g["makespan"][k + 1])
+        recs.append(out)
+    for (r0, x0), (r1, x1) in zip(*recs):
+        assert np.array_equal(r0, r1) and np.array_equal(x0, x1)
