@@ -165,17 +165,21 @@ int l2s_poll_error(l2s_handle h, int* instance_out, void* stream);
 
 /* ---- stateless evaluator (drop-in for Evaluator.forward) ------------------------------------------- */
 
-/* Bytes of scratch the caller must provide for a batch of `batch` graphs. */
+/* Bytes of scratch the caller must provide for a batch of `batch` graphs (16-byte aligned device memory). */
 int64_t l2s_eval_coo_workspace_bytes(int n_j, int n_m, int64_t batch);
 
 /* edge_index [2,E] int64 COO in any order (conjunctive + machine arcs of `batch` complete selections),
  * duration [batch*(n+2)] int32 or int64 (`duration_is_i64`), outputs est/lst [batch*(n+2)] and
- * makespan [batch] as float32 (integer valued, like the reference).  status_flag: one int32 on the
- * device that the CALLER zeroes; it is set (and then left) to a negative l2s_status if an input is not a batch
- * of acyclic complete JSSP selections -- check it after every call or once after many. */
+ * makespan [batch] as float32 (integer valued, like the reference).
+ * workspace: every call hands it back ZERO-FILLED (for any shape).  workspace_is_clean != 0 states that it already
+ * is zero-filled on entry (a cudaMemset once after allocation, or any earlier call on it) and saves the call its
+ * own memset; pass 0 when in doubt.
+ * status_flag: one int32 on the device that the CALLER zeroes; it is set (and then left) to a negative l2s_status if
+ * an input is not a batch of acyclic complete JSSP selections -- check it after every call or once after many. */
 int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duration, int duration_is_i64,
                  int n_j, int n_m, int64_t batch, float* est, float* lst, float* makespan,
-                 void* workspace, int64_t workspace_bytes, int32_t* status_flag, int device, void* stream);
+                 void* workspace, int64_t workspace_bytes, int workspace_is_clean, int32_t* status_flag, int device,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,7 @@ PROTOTYPES = {
     "l2s_poll_error": (C.c_int, [C.c_void_p, c_i32p, C.c_void_p]),
     "l2s_eval_coo_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int64]),
     "l2s_eval_coo": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64,
-                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
                                C.c_void_p]),
 }
 

@@ -551,20 +551,20 @@ int l2s_poll_error(l2s_handle h, int* instance_out, void* stream) {
 int64_t l2s_eval_coo_workspace_bytes(int n_j, int n_m, int64_t batch) {
   if (n_j < 1 || n_m < 1 || batch < 1) return L2S_ERR_INVALID_ARG;
   const long long node_stride = ru((long long)n_j * n_m + 2, 8);
-  const long long n1p = ru((long long)n_j * n_m + 2, 4);
-  return batch * node_stride * 2 + 16 + 2 * n1p * 4;
+  return batch * node_stride * 2 + 16;
 }
 
 int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duration, int duration_is_i64, int n_j,
                  int n_m, int64_t batch, float* est, float* lst, float* makespan, void* workspace,
-                 int64_t workspace_bytes, int32_t* status_flag, int device, void* stream) {
+                 int64_t workspace_bytes, int workspace_is_clean, int32_t* status_flag, int device, void* stream) {
   if (!edge_index || !duration || !est || !lst || !makespan || !workspace || !status_flag || batch < 1 ||
       n_j < 2 || n_m < 1 || n_edges < 0)
     return L2S_ERR_INVALID_ARG;
   const long long n = (long long)n_j * n_m;
   if (n + 2 > 65535 || n_m > 32) return L2S_ERR_UNSUPPORTED_SHAPE;
   if (batch * (n + 2) >= (1ll << 31)) return L2S_ERR_INVALID_ARG;   // 32-bit node ids per call
-  if (workspace_bytes < l2s_eval_coo_workspace_bytes(n_j, n_m, batch)) return L2S_ERR_INVALID_ARG;
+  if (workspace_bytes < l2s_eval_coo_workspace_bytes(n_j, n_m, batch) || ((unsigned long long)workspace & 15ull))
+    return L2S_ERR_INVALID_ARG;
   // a batch of complete selections has exactly this many edges (duplicates are caught on the device)
   if (n_edges != batch * ((long long)n_j * (n_m + 1) + (long long)n_m * (n_j - 1))) return L2S_ERR_BAD_GRAPH;
   CU(cudaSetDevice(device));
@@ -581,7 +581,6 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   const size_t links = (size_t)batch * L.node_stride * 2;
   a.ws.msucc = (uint16_t*)workspace;
   a.ws.conj_count = (unsigned long long*)((char*)workspace + links);
-  a.ws.pending_page = (int32_t*)((char*)workspace + links + 16);
   a.ws.flag = status_flag;
   a.est = est; a.lst = lst; a.ms = makespan;
   a.expect_conj = batch * ((long long)n_j * (n_m + 1));
@@ -600,7 +599,7 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
     CU(cudaFuncSetAttribute(coo_eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[device] = true;
   }
-  CU(cudaMemsetAsync(workspace, 0, links + 16, s));
+  if (!workspace_is_clean) CU(cudaMemsetAsync(workspace, 0, links + 16, s));
   CooIngestArgs g;
   memset(&g, 0, sizeof(g));
   g.ei = (const long long*)edge_index;
@@ -609,7 +608,6 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   g.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   g.ws = a.ws;
   g.lim = (unsigned)(batch * (n + 2));
-  g.page_words = 2 * L.n1p;
   g.vec_ok = (n_edges % 2 == 0) && (((unsigned long long)edge_index & 15ull) == 0);
   const long long items = g.vec_ok ? n_edges / 2 : n_edges;           // loads per row
   long long blocks = (items + 256 * kIngestTrips - 1) / (256 * kIngestTrips);

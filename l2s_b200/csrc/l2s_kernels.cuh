@@ -991,7 +991,6 @@ struct CooWs {
   uint16_t* msucc;      // [B][node_stride]
   unsigned long long* conj_count;
   int32_t* flag;        // device status word
-  int32_t* pending_page; // [2*n1p] words of -1 (written by the ingest kernel): TMA source for the tq sentinels
 };
 
 struct CooIngestArgs {
@@ -1000,7 +999,6 @@ struct CooIngestArgs {
   int n_j, n_m, n, n1, node_stride;
   unsigned magic_n1, magic_nm;   // floor(2^32 / d) + 1, see fast_div
   unsigned lim;                  // batch * (n+2)
-  int page_words;                // 2*n1p
   int vec_ok;                    // rows 16-byte aligned and E even: 2 edges per load
   CooWs ws;
 };
@@ -1076,8 +1074,6 @@ __global__ void __launch_bounds__(256) coo_ingest_kernel(const __grid_constant__
     }
   }
   if (bad) atomicCAS(a.ws.flag, 0, -5);
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < a.page_words; i += 256) a.ws.pending_page[i] = -1;
   // one atomic per CTA
   __shared__ int warp_sums[8];
   for (int o = 16; o; o >>= 1) conj += __shfl_xor_sync(kFull, conj, o);
@@ -1117,7 +1113,10 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   const uint32_t durw = base + a.off_durw;                               // uint16 [node_stride] node words
   const int n = L.n, n1 = L.n1, n_m = L.n_m, n_j = L.n_j;
   TL(0); TL(2);
-  if (b == 0 && lane == 0 && *a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
+  if (b == 0 && lane == 0) {
+    if (*a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
+    *a.ws.conj_count = 0ull;   // the workspace is handed back zero-filled (see l2s_eval_coo)
+  }
 
   // stage: machine successors (and, for the plain path, the "pending" sentinels) by TMA bulk copies issued by one
   // lane.  Durations: when the int64 rows are 16-byte aligned they are bulk-copied RAW into tq (8*n1 <= 8*n1p bytes)
@@ -1125,18 +1124,17 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   // is in flight while the warp works; otherwise they are loaded and converted here.
   const uint32_t bar = base + a.off_bar, bar2 = bar + 8u;
   if (lane == 0) {
-    const uint32_t sbytes = (uint32_t)L.node_stride * 2u, tbytes = 2u * (uint32_t)L.n1p * 4u;
+    const uint32_t sbytes = (uint32_t)L.node_stride * 2u;
     mbar_init(bar, 1);
     mbar_init(bar2, 1);
-    mbar_expect_tx(bar, sbytes + (a.dur_tma ? 0u : tbytes));
+    mbar_expect_tx(bar, sbytes);
     bulk_g2s(succ, a.ws.msucc + b * L.node_stride, sbytes, bar);
     if (a.dur_tma) {
       mbar_expect_tx(bar2, (uint32_t)n1 * 8u);
       bulk_g2s(s.tq, reinterpret_cast<const long long*>(a.duration) + b * n1, (uint32_t)n1 * 8u, bar2);
-    } else {
-      bulk_g2s(s.tq, a.ws.pending_page, tbytes, bar);
     }
   }
+  if (!a.dur_tma) fill_pending(L, s, lane, true);   // tq is free: "pending" sentinels right away
   int bad = 0;
   // node word of node i from its duration d; pos = (i-1) mod n_m
   auto node_word = [&](int i, long long d, int pos) -> int {
@@ -1176,6 +1174,10 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   TL(3);   // durations converted (plain path)
   mbar_wait(bar, 0);
   TL(4);   // staged
+  {   // the successors are in shared memory: hand the row of the workspace back zero-filled
+    uint4* grow = reinterpret_cast<uint4*>(a.ws.msucc + b * L.node_stride);
+    for (int i = lane; i < L.node_stride / 8; i += 32) grow[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   // heads = operations nobody points to.  One flag BYTE per node in the (still unused) walk words: plain stores, no
   // atomics (a bitmap needed shared-memory atomics on a handful of words: ~10-way serialised)
   const uint32_t flags = s.walk;                      // n1 bytes <= 4*walk_stride bytes

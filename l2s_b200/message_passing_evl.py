@@ -50,7 +50,7 @@ class Evaluator:
         need = self._lib.l2s_eval_coo_workspace_bytes(n_j, n_m, B)
         _capi.check(need, "l2s_eval_coo_workspace_bytes")
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=device)   # every call hands it back zero-filled
             self._flag = torch.zeros(1, dtype=torch.int32, device=device)
             self._sticky = torch.zeros(1, dtype=torch.int32, device=device)
         if self.strict:
@@ -62,7 +62,7 @@ class Evaluator:
         _capi.check(self._lib.l2s_eval_coo(
             C.c_void_p(ei.data_ptr()), ei.shape[1], C.c_void_p(dur.data_ptr()), 1 if dur.dtype == torch.int64 else 0,
             n_j, n_m, B, C.c_void_p(est.data_ptr()), C.c_void_p(lst.data_ptr()), C.c_void_p(ms.data_ptr()),
-            C.c_void_p(self._ws.data_ptr()), self._ws.numel(),
+            C.c_void_p(self._ws.data_ptr()), self._ws.numel(), 1,
             C.c_void_p((self._flag if self.strict else self._sticky).data_ptr()),
             device.index if device.index is not None else torch.cuda.current_device(), stream), "l2s_eval_coo")
         if self.strict:

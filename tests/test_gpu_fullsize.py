@@ -228,3 +228,30 @@ def test_randomised_shapes_and_durations_against_c_oracle():
             for b in range(B):
                 want = cenv.pairs[b, :cenv.npairs[b]].tolist() if cenv.npairs[b] else [[0, 0]]
                 assert fa[b] == want, "case %d step %d instance %d pairs" % (case, k, b)
+
+
+def test_evaluator_workspace_is_handed_back_clean():
+    """One Evaluator (one workspace) across shapes, int32 / int64 durations and rejected inputs: every call leaves
+    the workspace zero-filled, so the next one -- which skips its memset -- is still exact."""
+    from l2s_b200 import Evaluator, JsspN5, L2SError
+    ev = Evaluator()
+    for rnd, (n_j, n_m, B) in enumerate([(20, 15, 64), (10, 10, 200), (15, 15, 33), (20, 15, 64), (6, 6, 500)]):
+        inst = gen_instances(n_j, n_m, B, seed=11 + rnd)
+        env = JsspN5(n_j, n_m, 1, 99)
+        env.reset(inst, "fdd-divide-mwkr", "cuda")
+        env.run("random", 7, seed=rnd)
+        state, fa, done = env.observe()
+        ex = env.export_state()
+        n1 = n_j * n_m + 2
+        ei = torch.cat([state[1], state[2]], dim=1)
+        dur = torch.zeros((B, n1), dtype=torch.int64 if rnd % 2 == 0 else torch.int32, device="cuda")
+        dur[:, 1:-1] = torch.from_numpy(inst[:, 0].reshape(B, -1)).cuda().to(dur.dtype)
+        if rnd in (1, 3):        # a rejected call in between: duplicated machine arc
+            bad = ei.clone()
+            bad[:, -1] = bad[:, -2]
+            with pytest.raises(L2SError):
+                ev.forward(bad, dur.reshape(-1, 1), n_j, n_m)
+        est, lst, ms = ev.forward(ei, dur.reshape(-1, 1), n_j, n_m)
+        assert torch.equal(est.reshape(B, n1), ex["est"].float()) and torch.equal(lst.reshape(B, n1), ex["lst"].float())
+        assert torch.equal(ms, env.current_objs)
+        assert int(ev._ws.count_nonzero()) == 0
