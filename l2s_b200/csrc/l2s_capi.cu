@@ -168,14 +168,8 @@ int l2s_debug_levels(unsigned long long* out2, int reset) {   // {sum of levels,
 }
 #endif
 
-int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* out) {
-  if (!out || n_j < 2 || n_m < 1 || batch < 1 || pmax < 0) return L2S_ERR_INVALID_ARG;
-  if (pmax == 0) pmax = 32;
-  if (n_m > 32 || (long long)n_j * n_m + 2 > 65535) return L2S_ERR_UNSUPPORTED_SHAPE;
-  if ((long long)batch * ((long long)n_j * n_m + 2) >= (1ll << 31)) return L2S_ERR_INVALID_ARG;   // 32-bit node ids per slice
+static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int device) {
   CU(cudaSetDevice(device));
-  l2s_handle h = (l2s_handle)calloc(1, sizeof(l2s_handle_s));
-  if (!h) return L2S_ERR_INVALID_ARG;
   h->device = device;
   h->B = batch;
   h->pmax = pmax;
@@ -190,7 +184,7 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->run_stride = ru((long long)h->run_off_plist + (long long)pmax * 4, 16);
   // GREEDY with n_m <= 16 evaluates two neighbours per sweep and keeps a second copy of the walk words for that
   h->run_off_walk2 = n_m <= 16 ? (int)h->run_stride : -1;
-  h->run_stride_greedy = n_m <= 16 ? h->run_stride + (size_t)L.walk_stride * 4 : h->run_stride;
+  h->run_stride_greedy = n_m <= 16 ? h->run_stride + (size_t)L.walk_stride * 4 + 16 : h->run_stride;   // +16: a sweep prefetches one word past its last row
   // initial-solution builder layout
   {
     InitLayout& I = h->IL;
@@ -211,7 +205,7 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->warps_run_greedy = pick_warps(h->run_stride_greedy);
   if (!h->warps_run_greedy) { h->warps_run_greedy = h->warps_run; h->run_stride_greedy = h->run_stride; h->run_off_walk2 = -1; }
   h->warps_init = pick_warps(h->IL.bytes);
-  if (!h->warps_step || !h->warps_run || !h->warps_init) { free(h); return L2S_ERR_UNSUPPORTED_SHAPE; }
+  if (!h->warps_step || !h->warps_run || !h->warps_init) return L2S_ERR_UNSUPPORTED_SHAPE;
   // few instances per SM (large graphs): give every instance a whole CTA so that the SM is not left idle
   {
     const long long per_sm = (long long)(kSmemPerSm / ((size_t)L.bytes + kSmemCtaReserve));
@@ -278,6 +272,25 @@ int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* ou
   h->rec_direct = 1;
   if (const char* e = getenv("L2S_HOST_ZEROCOPY")) h->zero_copy = atoi(e) != 0;
   if (const char* e = getenv("L2S_HOST_RECORDS")) h->rec_direct = atoi(e) != 0;
+  return L2S_OK;
+}
+
+
+int l2s_destroy(l2s_handle h);
+
+int l2s_create(int n_j, int n_m, int batch, int pmax, int device, l2s_handle* out) {
+  if (!out || n_j < 2 || n_m < 1 || batch < 1 || pmax < 0) return L2S_ERR_INVALID_ARG;
+  if (pmax == 0) pmax = 32;
+  if (n_m > 32 || (long long)n_j * n_m + 2 > 65535) return L2S_ERR_UNSUPPORTED_SHAPE;
+  if ((long long)batch * ((long long)n_j * n_m + 2) >= (1ll << 31)) return L2S_ERR_INVALID_ARG;   // 32-bit node ids per slice
+  l2s_handle h = (l2s_handle)calloc(1, sizeof(l2s_handle_s));
+  if (!h) return L2S_ERR_INVALID_ARG;
+  h->device = device;
+  const int r = create_into(h, n_j, n_m, batch, pmax, device);
+  if (r != L2S_OK) {   // release whatever was allocated before the failure
+    l2s_destroy(h);
+    return r;
+  }
   *out = h;
   return L2S_OK;
 }

@@ -15,12 +15,12 @@
 // State format ("walk words"): the processing order of machine m is the row walk[m*n_j .. m*n_j+n_j) of
 // 32-bit words, one per operation:
 //     bits  0..15  node id (1..n)
-//     bits 16..27  duration (<= 4095)
-//     bit  28      first operation of its job   (job predecessor = S)
-//     bit  29      last operation of its job    (job successor = T)
-//     bit  30      "jobfirst": the job predecessor precedes the machine predecessor in networkx's
+//     bit  16      first operation of its job   (job predecessor = S)
+//     bit  17      last operation of its job    (job successor = T)
+//     bit  18      "jobfirst": the job predecessor precedes the machine predecessor in networkx's
 //                  insertion order (set when a swap re-adds the machine in-edge)
-//     bit  31      last position of its machine row
+//     bit  19      last position of its machine row
+//     bits 20..31  duration (<= 4095; the top bits, so that a sweep extracts it with one shift)
 // so that one shared-memory load gives a walker everything about its next operation.  where[v] is the index
 // of node v's word.
 #pragma once
@@ -36,11 +36,11 @@ constexpr int kLastFlag = 0x4000;
 constexpr int kDurMask = 0x0FFF;
 // walk words
 constexpr unsigned kWId = 0xffffu;
-constexpr int kWDurShift = 16;
-constexpr unsigned kWFirst = 1u << 28;
-constexpr unsigned kWLast = 1u << 29;
-constexpr unsigned kWJf = 1u << 30;
-constexpr unsigned kWRowEnd = 1u << 31;
+constexpr int kWDurShift = 20;
+constexpr unsigned kWFirst = 1u << 16;
+constexpr unsigned kWLast = 1u << 17;
+constexpr unsigned kWJf = 1u << 18;
+constexpr unsigned kWRowEnd = 1u << 19;
 constexpr unsigned kFull = 0xffffffffu;
 
 __host__ __device__ __forceinline__ unsigned make_walk(int v, int durw, bool jf, bool rowend) {
@@ -227,13 +227,14 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
   // One level: place the lane's next operation if its job neighbour is final.  Straight-line (predicated)
   // code: the warp stays converged, so shared-memory writes of one level are visible to the next.
   auto level = [&]() {
-    // Hand-scheduled: 21 instructions, fully predicated.  Equivalent C:
+    // Hand-scheduled: 20 instructions, fully predicated.  Equivalent C:
     //   a = a_nb + 4*(w & 0xffff); nb = left > 0 ? tq[a] : -1; if (w & bflag) nb = 0;
     //   adv = left > 0 && nb >= 0; val = max(prevval, nb) + dur(w);
-    //   if (adv) { tq[a + dself] = val; prevval = val; w = wn; a_w += stepb; --left; if (left > 1) wn = walk[a_w + stepb]; }
+    //   if (adv) { tq[a + dself] = val; prevval = val; w = wn; a_w += stepb; --left; wn = walk[a_w + stepb]; }
+    //   (the prefetch past the end of a row reads a neighbouring word of the instance's own shared memory: never used)
     asm volatile(
         "{\n\t"
-        ".reg .pred pa, pb, pv, pl;\n\t"
+        ".reg .pred pa, pb, pv;\n\t"
         ".reg .b32 a, nb, t, d, val;\n\t"
         "setp.gt.s32 pa, %2, 0;\n\t"
         "and.b32 a, %0, 0xffff;\n\t"
@@ -244,7 +245,7 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
         "setp.ne.u32 pb, t, 0;\n\t"
         "selp.b32 nb, 0, nb, pb;\n\t"
         "setp.ge.and.s32 pv, nb, 0, pa;\n\t"
-        "bfe.u32 d, %0, 16, 12;\n\t"
+        "shr.u32 d, %0, 20;\n\t"
         "max.s32 val, %3, nb;\n\t"
         "add.s32 val, val, d;\n\t"
         "add.s32 a, a, %7;\n\t"
@@ -253,9 +254,8 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
         "@pv mov.b32 %0, %1;\n\t"
         "@pv add.s32 %4, %4, %7;\n\t"
         "@pv add.s32 %2, %2, -1;\n\t"
-        "setp.gt.and.s32 pl, %2, 1, pv;\n\t"
         "add.s32 t, %4, %7;\n\t"
-        "@pl ld.shared.b32 %1, [t];\n\t"
+        "@pv ld.shared.b32 %1, [t];\n\t"
         "}\n"
         : "+r"(w), "+r"(wn), "+r"(left), "+r"(prevval), "+r"(a_w)
         : "r"(a_nb), "r"(bflag), "r"(stepb)
