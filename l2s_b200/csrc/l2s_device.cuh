@@ -208,6 +208,7 @@ __device__ unsigned long long g_dbg_levels[2] = {0ull, 0ull};   // diagnostic bu
 // half / walk: which half of tq the lane's values live in and which copy of the walk words it reads (defaults:
 // half = dir, the instance's own walk words); the greedy policy evaluates two neighbours at once with both
 // half-warps sweeping FORWARD, each in its own tq half over its own copy of the walk words.
+template <bool kOnePtr = false>
 __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m, int dir, bool active, int& last,
                                           int half = -1, uint32_t walk = 0u) {
   const int n_j = L.n_j;
@@ -223,43 +224,77 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
   unsigned w = 0, wn = 0;
   if (left > 0) w = (unsigned)lds32(a_w);
   if (left > 1) wn = (unsigned)lds32(a_w + stepb);
+  // kOnePtr (per-lane direction, step in a register): a_w becomes the address of the word that turns into `wn` at
+  // the next placement, which saves an add per level; with a compile-time direction the +-4 folds into the load
+  // and the two-pointer form schedules better (measured: 30x20 1.9 % faster)
+  if (kOnePtr) a_w += 2 * stepb;
   int budget = (L.n + 3) >> 1;  // a DAG needs at most n levels; two levels per trip
   // One level: place the lane's next operation if its job neighbour is final.  Straight-line (predicated)
   // code: the warp stays converged, so shared-memory writes of one level are visible to the next.
   auto level = [&]() {
-    // Hand-scheduled: 20 instructions, fully predicated.  Equivalent C:
+    // Hand-scheduled: 19-20 instructions, fully predicated.  Equivalent C:
     //   a = a_nb + 4*(w & 0xffff); nb = left > 0 ? tq[a] : -1; if (w & bflag) nb = 0;
     //   adv = left > 0 && nb >= 0; val = max(prevval, nb) + dur(w);
     //   if (adv) { tq[a + dself] = val; prevval = val; w = wn; a_w += stepb; --left; wn = walk[a_w + stepb]; }
     //   (the prefetch past the end of a row reads a neighbouring word of the instance's own shared memory: never used)
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pa, pb, pv;\n\t"
-        ".reg .b32 a, nb, t, d, val;\n\t"
-        "setp.gt.s32 pa, %2, 0;\n\t"
-        "and.b32 a, %0, 0xffff;\n\t"
-        "mad.lo.u32 a, a, 4, %5;\n\t"
-        "mov.b32 nb, -1;\n\t"
-        "@pa ld.shared.b32 nb, [a];\n\t"
-        "and.b32 t, %0, %6;\n\t"
-        "setp.ne.u32 pb, t, 0;\n\t"
-        "selp.b32 nb, 0, nb, pb;\n\t"
-        "setp.ge.and.s32 pv, nb, 0, pa;\n\t"
-        "shr.u32 d, %0, 20;\n\t"
-        "max.s32 val, %3, nb;\n\t"
-        "add.s32 val, val, d;\n\t"
-        "add.s32 a, a, %7;\n\t"
-        "@pv st.shared.b32 [a], val;\n\t"
-        "@pv mov.b32 %3, val;\n\t"
-        "@pv mov.b32 %0, %1;\n\t"
-        "@pv add.s32 %4, %4, %7;\n\t"
-        "@pv add.s32 %2, %2, -1;\n\t"
-        "add.s32 t, %4, %7;\n\t"
-        "@pv ld.shared.b32 %1, [t];\n\t"
-        "}\n"
-        : "+r"(w), "+r"(wn), "+r"(left), "+r"(prevval), "+r"(a_w)
-        : "r"(a_nb), "r"(bflag), "r"(stepb)
-        : "memory");
+    if (kOnePtr) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred pa, pb, pv;\n\t"
+          ".reg .b32 a, nb, t, d, val;\n\t"
+          "setp.gt.s32 pa, %2, 0;\n\t"
+          "and.b32 a, %0, 0xffff;\n\t"
+          "mad.lo.u32 a, a, 4, %5;\n\t"
+          "mov.b32 nb, -1;\n\t"
+          "@pa ld.shared.b32 nb, [a];\n\t"
+          "and.b32 t, %0, %6;\n\t"
+          "setp.ne.u32 pb, t, 0;\n\t"
+          "selp.b32 nb, 0, nb, pb;\n\t"
+          "setp.ge.and.s32 pv, nb, 0, pa;\n\t"
+          "shr.u32 d, %0, 20;\n\t"
+          "max.s32 val, %3, nb;\n\t"
+          "add.s32 val, val, d;\n\t"
+          "add.s32 a, a, %7;\n\t"
+          "@pv st.shared.b32 [a], val;\n\t"
+          "@pv mov.b32 %3, val;\n\t"
+          "@pv mov.b32 %0, %1;\n\t"
+          "@pv add.s32 %2, %2, -1;\n\t"
+          "@pv ld.shared.b32 %1, [%4];\n\t"
+          "@pv add.s32 %4, %4, %7;\n\t"
+          "}\n"
+          : "+r"(w), "+r"(wn), "+r"(left), "+r"(prevval), "+r"(a_w)
+          : "r"(a_nb), "r"(bflag), "r"(stepb)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred pa, pb, pv;\n\t"
+          ".reg .b32 a, nb, t, d, val;\n\t"
+          "setp.gt.s32 pa, %2, 0;\n\t"
+          "and.b32 a, %0, 0xffff;\n\t"
+          "mad.lo.u32 a, a, 4, %5;\n\t"
+          "mov.b32 nb, -1;\n\t"
+          "@pa ld.shared.b32 nb, [a];\n\t"
+          "and.b32 t, %0, %6;\n\t"
+          "setp.ne.u32 pb, t, 0;\n\t"
+          "selp.b32 nb, 0, nb, pb;\n\t"
+          "setp.ge.and.s32 pv, nb, 0, pa;\n\t"
+          "shr.u32 d, %0, 20;\n\t"
+          "max.s32 val, %3, nb;\n\t"
+          "add.s32 val, val, d;\n\t"
+          "add.s32 a, a, %7;\n\t"
+          "@pv st.shared.b32 [a], val;\n\t"
+          "@pv mov.b32 %3, val;\n\t"
+          "@pv mov.b32 %0, %1;\n\t"
+          "@pv add.s32 %4, %4, %7;\n\t"
+          "@pv add.s32 %2, %2, -1;\n\t"
+          "add.s32 t, %4, %7;\n\t"
+          "@pv ld.shared.b32 %1, [t];\n\t"
+          "}\n"
+          : "+r"(w), "+r"(wn), "+r"(left), "+r"(prevval), "+r"(a_w)
+          : "r"(a_nb), "r"(bflag), "r"(stepb)
+          : "memory");
+    }
     __syncwarp();
   };
 #ifdef L2S_TIMELINE
@@ -286,7 +321,7 @@ __device__ __forceinline__ int evaluate_instance(const Layout& L, const Inst& s,
   int fwd_last = 0;
   if (L.n_m <= 16 && need_q) {
     const int m = lane & 15, dir = lane >> 4;
-    ok = wavefront(L, s, m, dir, m < L.n_m, last);
+    ok = wavefront<true>(L, s, m, dir, m < L.n_m, last);
     fwd_last = dir ? 0 : last;
   } else {
     ok = wavefront(L, s, lane, 0, lane < L.n_m, last);
