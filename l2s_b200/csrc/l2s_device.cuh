@@ -351,7 +351,10 @@ __device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, uint32
     const unsigned jp = v - 1u;
     const int fj = (w & kWFirst) ? -1 : lds32(s.tq + 4u * jp);     // completion of the job predecessor
     const int fm = mp ? lds32(s.tq + 4u * mp) : -1;
-    const bool take_jp = (fj >= 0) & ((fm < 0) | (fj > fm) | ((fj == fm) & (((w & kWJf) != 0u) | (jp < mp))));
+    // job predecessor wins iff it exists and (fj, tie) > (fm, 0) lexicographically, tie = listed first in G.pred[v]
+    // (fm = -1 when there is no machine predecessor); one integer comparison of 2*f + tie (f < 2^24)
+    const int tie = (((w & kWJf) != 0u) | (jp < mp)) ? 1 : 0;
+    const bool take_jp = (fj >= 0) & (2 * fj + tie > 2 * fm);
     sts16(s.crit + 2u * v, (int)(take_jp ? jp : mp));
     if (kMsu) {   // msu[v] = machine successor (0 = none), node-indexed, for the ascending-source edge list
       const unsigned ms = (w & kWRowEnd) ? 0u : ((unsigned)lds32(s.walk + 4u * (i + 1)) & kWId);
