@@ -324,10 +324,17 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   TL(0); TL(2);
   int a0 = 0, a1 = 0;
   if (a.actions && !a.export_only) {
-    a0 = a.actions[2 * b];
-    a1 = a.actions[2 * b + 1];
+    if ((reinterpret_cast<uintptr_t>(a.actions) & 7u) == 0) {   // [B,2] int32 rows: one 8-byte load
+      const int2 act = reinterpret_cast<const int2*>(a.actions)[b];
+      a0 = act.x;
+      a1 = act.y;
+    } else {
+      a0 = a.actions[2 * b];
+      a1 = a.actions[2 * b + 1];
+    }
   }
-  int tabu0 = a.st.tabu[2 * b], tabu1 = a.st.tabu[2 * b + 1];
+  const int2 tabu_in = reinterpret_cast<const int2*>(a.st.tabu)[b];
+  int tabu0 = tabu_in.x, tabu1 = tabu_in.y;
   const int inc_in = a.st.inc[b], cur_in = a.st.cur[b];
   stage_instance(L, s, a.st, b, lane, true);
   TL(11);   // staged
@@ -336,8 +343,13 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   // looking up a0's machine row first costs a dependent global load and measured 5 % slower)
   int i0 = -1;
   if (a0 >= 1 && a0 <= n) {
-    for (int i = lane; i < n; i += 32)
-      if ((lds32(s.walk + 4u * i) & (int)kWId) == a0) i0 = i;
+    for (int i = 4 * lane; i < L.walk_stride; i += 128) {   // four walk words per lane and trip (the padding is 0)
+      const uint4 wq = lds128(s.walk + 4u * i);
+      if ((int)(wq.x & kWId) == a0) i0 = i;
+      if ((int)(wq.y & kWId) == a0) i0 = i + 1;
+      if ((int)(wq.z & kWId) == a0) i0 = i + 2;
+      if ((int)(wq.w & kWId) == a0) i0 = i + 3;
+    }
     i0 = __reduce_max_sync(kFull, i0);
   }
 
@@ -405,8 +417,9 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
       // common case (one FMA residual correction reproduces the IEEE quotient, verified on the host; even node
       // count => 8-byte aligned rows): two adjacent nodes per lane, 64-bit shared loads, 64-bit global stores
       const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
-      float2* xo2 = reinterpret_cast<float2*>(a.x + (size_t)b * n1 * 3) + 3 * lane;
-      for (int p = lane; p < (n1 >> 1); p += 32, xo2 += 96) {
+      float2* const xb = reinterpret_cast<float2*>(a.x + (size_t)b * n1 * 3);
+      for (int p = lane; p < (n1 >> 1); p += 32) {
+        float2* const xo2 = xb + 3 * p;
         const unsigned dw = (unsigned)lds32(s.durw + 4u * p);
         const int2 f = lds64(fin + 8u * p), t = lds64(q + 8u * p);
         const int d0 = (int)(dw & kDurMask), d1 = (int)((dw >> 16) & kDurMask);
