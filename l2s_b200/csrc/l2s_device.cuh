@@ -215,7 +215,7 @@ __device__ unsigned long long g_dbg_levels[2] = {0ull, 0ull};   // diagnostic bu
 // half-warps sweeping FORWARD, each in its own tq half over its own copy of the walk words.
 template <bool kOnePtr = false>
 __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m, int dir, bool active, int& last,
-                                          int half = -1, uint32_t walk = 0u) {
+                                          int half = -1, uint32_t walk = 0u, int start = 0, int prev0 = 0) {
   const int n_j = L.n_j;
   if (half < 0) half = dir;
   if (walk == 0u) walk = s.walk;
@@ -223,9 +223,11 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
   const uint32_t a_nb = dir ? a_self + 4u : a_self - 4u;             // &tq[base +- 1]
   const unsigned bflag = dir ? kWLast : kWFirst;
   const int stepb = dir ? -4 : 4;                                    // walk step in bytes; also a_self - a_nb
-  uint32_t a_w = walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 : 0));
-  int left = active ? n_j : 0;                                       // operations still to place
-  int prevval = 0;
+  // start / prev0 (forward only): resume the lane's row at position `start` with its machine predecessor's value
+  // prev0 (incremental re-evaluation: the operations before `start` keep their values)
+  uint32_t a_w = walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 : start));
+  int left = active ? n_j - start : 0;                               // operations still to place
+  int prevval = prev0;
   unsigned w = 0, wn = 0;
   if (left > 0) w = (unsigned)lds32(a_w);
   if (left > 1) wn = (unsigned)lds32(a_w + stepb);
@@ -337,6 +339,48 @@ __device__ __forceinline__ int evaluate_instance(const Layout& L, const Inst& s,
     }
   }
   const int ms = __reduce_max_sync(kFull, fwd_last);
+  return ok ? ms : -1;
+}
+
+// Incremental forward re-evaluation after the adjacent pair at walk positions i0, i0+1 was swapped, for callers that
+// kept the completion times of the previous evaluation in tq's forward half (the fused K-step kernel).
+// Every operation whose value can change is a descendant of the pair, so its earliest start -- before and after the
+// move -- is >= t0 = completion of the pair's machine predecessor (0 at a row start).  Operations with an old
+// earliest start < t0 therefore keep their values (the set is closed under predecessors); along a machine row
+// earliest starts increase, so these are a prefix of every row: each lane finds its prefix by binary search, the
+// other completion times go back to "pending", and the sweep resumes every row behind its prefix.
+__device__ __forceinline__ int evaluate_forward_from(const Layout& L, const Inst& s, int lane, int i0) {
+  const int n_j = L.n_j;
+  const uint32_t fin = s.tq;
+  int t0 = 0;
+  {
+    const unsigned wp = i0 > 0 ? (unsigned)lds32(s.walk + 4u * (i0 - 1)) : kWRowEnd;
+    if (!(wp & kWRowEnd)) t0 = lds32(fin + 4u * (wp & kWId));
+  }
+  const bool active = lane < L.n_m;
+  const uint32_t row = s.walk + 4u * (uint32_t)((active ? lane : 0) * n_j);
+  int lo = 0, hi = n_j;
+  for (int span = n_j; span > 0; span >>= 1) {   // uniform trip count >= ceil(log2(n_j + 1))
+    if (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const unsigned w = (unsigned)lds32(row + 4u * mid);
+      const int est = lds32(fin + 4u * (w & kWId)) - (int)(w >> kWDurShift);
+      if (est < t0) lo = mid + 1; else hi = mid;
+    }
+  }
+  const int start = lo;
+  int prev0 = 0;
+  if (start > 0) prev0 = lds32(fin + 4u * ((unsigned)lds32(row + 4u * (start - 1)) & kWId));
+  __syncwarp();
+  for (int i = lane; i < L.n; i += 32) {
+    const unsigned w = (unsigned)lds32(s.walk + 4u * i);
+    const uint32_t af = fin + 4u * (w & kWId);
+    if (lds32(af) - (int)(w >> kWDurShift) >= t0) sts32(af, -1);
+  }
+  __syncwarp();
+  int last = 0;
+  const bool ok = wavefront(L, s, lane, 0, active, last, -1, 0u, start, prev0);
+  const int ms = __reduce_max_sync(kFull, last);
   return ok ? ms : -1;
 }
 

@@ -959,9 +959,15 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
         status = r;
       }
       if (!status && r == 0) {   // a dummy move leaves the schedule, its makespan and its move set unchanged
-        fill_pending(L, s, lane, false);
-        __syncwarp();
-        ms = evaluate_instance(L, s, lane, false);
+        if (a.policy != 2 && L.n_m <= 32) {
+          // REPLAY / RANDOM: tq's forward half still holds the completion times of the previous evaluation:
+          // only the part of the schedule behind the swapped pair is swept again
+          ms = evaluate_forward_from(L, s, lane, i0);
+        } else {   // GREEDY: the trial evaluations overwrote them
+          fill_pending(L, s, lane, false);
+          __syncwarp();
+          ms = evaluate_instance(L, s, lane, false);
+        }
         if (ms < 0) status = -5;
       }
       if (!status && r == 0) {
