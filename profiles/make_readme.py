@@ -45,7 +45,7 @@ with open('profiles/README_r1.md', 'w') as f:
 
 All numbers come from runs on the GPU box via `gpurun`; bench values are never taken under ncu.
 Files: `bench_r1_1gpu.json`, `bench_r1_8gpu.json` (bench lines), `launches_r1_bench_steps40.csv` (ncu launch list),
-`step_kernel_traffic.json` (DRAM bytes per launch from the `--set full` capture), `by_phase.py` / `by_line.py` /
+`step_kernel_traffic.json` (DRAM bytes per launch from the `--set full` capture), `step_kernel_ncu_details_r1.txt` / `step_kernel_ncu_raw_r1.csv` (details and raw pages of that capture, exported with `ncu -i`), `timeline.py` / `timeline_eval.py` (+ `timeline_r1.txt`, `timeline_eval_r1.txt`), `shapes_r1.txt`, `by_phase.py` / `by_line.py` /
 `sass_of.py` / `raw_metrics.py` / `make_readme.py` (the scripts that produced the tables below from the `.ncu-rep` exports).
 
 ## Bench line (`python bench.py`, defaults: 2000 steps, 8 warm-up)
