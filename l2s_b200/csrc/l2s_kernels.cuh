@@ -578,13 +578,16 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   // for the feature loop NOW (clamped index: no select that would wait for the data), so that the loads are in
   // flight during staging and the sweeps instead of being a chain of dependent global-load latencies inside that
   // loop (measured at 100x20: 9-11 us -> 1-3 us)
-  constexpr int kDurRegs = 16;
+  constexpr int kPairRegs = 8;
   const uint16_t* gdurw = a.st.durw + (size_t)b * L.node_stride;
-  const bool dur_in_regs = (n1 + nthr - 1) / nthr <= kDurRegs;
-  int dreg[kDurRegs];
-  if (dur_in_regs && a.x) {
+  // fast feature path: both divisors pass the one-correction test, even node count (8-byte aligned rows), and a
+  // thread's share of node-word PAIRS fits the registers
+  const bool x_fast = a.x && a.div_high == 1 && a.div_fea == 1 && !(n1 & 1) && ((n1 >> 1) + nthr - 1) / nthr <= kPairRegs;
+  unsigned dpair[kPairRegs];
+  if (x_fast) {
 #pragma unroll
-    for (int k = 0; k < kDurRegs; ++k) dreg[k] = (int)__ldg(gdurw + min(tid + k * nthr, n1 - 1));
+    for (int k = 0; k < kPairRegs; ++k)
+      dpair[k] = __ldg(reinterpret_cast<const unsigned*>(gdurw) + min(tid + k * nthr, (n1 >> 1) - 1));
   }
   stage_instance(L, s, a.st, b, tid, true, nthr);
   __syncthreads();
@@ -667,16 +670,25 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   if (a.x) {
     float* xo = a.x + (size_t)b * n1 * 3;
     const float fms = (float)ms;
-    if (dur_in_regs) {
+    if (x_fast) {
+      // two adjacent nodes per thread: 64-bit shared loads, 64-bit global stores, one FMA residual correction
+      const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
+      float2* const xb = reinterpret_cast<float2*>(xo);
 #pragma unroll
-      for (int k = 0; k < kDurRegs; ++k) {
-        const int i = tid + k * nthr;
-        if (i < n1) {
-          const int d = dreg[k] & kDurMask;
-          const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
-          xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
-          xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
-          xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
+      for (int k = 0; k < kPairRegs; ++k) {
+        const int p = tid + k * nthr;
+        if (p < (n1 >> 1)) {
+          const unsigned dw = dpair[k];
+          const int2 f = lds64(fin + 8u * p), t = lds64(q + 8u * p);
+          const int d0 = (int)(dw & kDurMask), d1 = (int)((dw >> 16) & kDurMask);
+          const float fd0 = (float)d0, fe0 = (float)(f.x - d0), fl0 = fms - (float)t.x;
+          const float fd1 = (float)d1, fe1 = (float)(f.y - d1), fl1 = fms - (float)t.y;
+          const float q00 = __fmul_rn(fd0, rh), q01 = __fmul_rn(fe0, rf), q02 = __fmul_rn(fl0, rf);
+          const float q10 = __fmul_rn(fd1, rh), q11 = __fmul_rn(fe1, rf), q12 = __fmul_rn(fl1, rf);
+          float2* const xo2 = xb + 3 * p;
+          xo2[0] = make_float2(__fmaf_rn(__fmaf_rn(-ch, q00, fd0), rh, q00), __fmaf_rn(__fmaf_rn(-cf, q01, fe0), rf, q01));
+          xo2[1] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q02, fl0), rf, q02), __fmaf_rn(__fmaf_rn(-ch, q10, fd1), rh, q10));
+          xo2[2] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q11, fe1), rf, q11), __fmaf_rn(__fmaf_rn(-cf, q12, fl1), rf, q12));
         }
       }
     } else {
