@@ -176,7 +176,11 @@ static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int 
   // kernel + layout choice: the warp-per-instance step kernel (with staged node words) if at least 16 such
   // instances fit an SM, else one CTA per instance
   h->L = make_layout(n_j, n_m, true, pmax);
-  const bool small = (long long)(kSmemPerSm / ((size_t)h->L.bytes + kSmemCtaReserve)) >= 16;
+  // With more than 16 machines the warp kernel runs its forward and backward sweeps one after the other, the CTA
+  // kernel side by side on two warps: for small batches (latency regime) the CTA kernel is the faster one there
+  // (30x20, 512 instances: 15.4 vs 18.5 us per step; equal at 4096; with n_m <= 16 the warp kernel wins at any batch)
+  const bool fits16 = (long long)(kSmemPerSm / ((size_t)h->L.bytes + kSmemCtaReserve)) >= 16;
+  const bool small = fits16 && (n_m <= 16 || ((long long)batch + 147) / 148 > 16);
   if (!small) h->L = make_layout(n_j, n_m, false, pmax);
   const Layout& L = h->L;
   h->run_off_where = L.bytes;
