@@ -691,6 +691,17 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
           xo2[2] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q11, fe1), rf, q11), __fmaf_rn(__fmaf_rn(-cf, q12, fl1), rf, q12));
         }
       }
+    } else if (a.div_high == 1 && a.div_fea == 1) {   // odd node count or a very large instance: node by node
+      const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
+#pragma unroll 4
+      for (int i = tid; i < n1; i += nthr) {
+        const int d = __ldg(gdurw + i) & kDurMask;
+        const float fd = (float)d, fe = (float)(lds32(fin + 4u * i) - d), fl = fms - (float)lds32(q + 4u * i);
+        const float q0 = __fmul_rn(fd, rh), q1 = __fmul_rn(fe, rf), q2 = __fmul_rn(fl, rf);
+        xo[3 * i] = __fmaf_rn(__fmaf_rn(-ch, q0, fd), rh, q0);
+        xo[3 * i + 1] = __fmaf_rn(__fmaf_rn(-cf, q1, fe), rf, q1);
+        xo[3 * i + 2] = __fmaf_rn(__fmaf_rn(-cf, q2, fl), rf, q2);
+      }
     } else {
 #pragma unroll 4
       for (int i = tid; i < n1; i += nthr) {
