@@ -42,6 +42,11 @@ UNIT = "inst-steps/s"
 REPLICAS = 4   # rotating independent batches so that the per-step working set exceeds the 126 MB L2
 
 
+def workload_name(shape, batch):
+    return ("syn%s U{1..98}, batch %d per GPU, fdd-divide-mwkr init, replayed random feasible N5 moves; one step = one "
+            "environment step (l2s_step launch) over the batch" % (shape, batch))
+
+
 def gen_instances(n_j, n_m, B, seed):
     """uni_instance_gen semantics (env/generateJSP.py:14-18), vectorised: durations randint(1, 99) ->
     U{1..98}; machine rows = independent permutations of 1..n_m."""
@@ -174,8 +179,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * units / rate / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "syn%s U{1..98} fdd-divide-mwkr, random feasible N5 moves" % args.shape,
-                   "batch_per_step": per * procs},
+        "config": {"workload": workload_name(args.shape, args.batch), "shape": args.shape, "batch_per_gpu": args.batch,
+                   "sample": "each timed step advances %d instances of that workload (bounded sample; throughput "
+                             "is per instance-step, so it does not depend on the batch size)" % (per * procs)},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": "%d processes x %d instances x %d env.step calls of the numpy/Python oracle port "
                                    "(oracle/l2s_oracle.py OracleEnv.step); the reference itself is pure Python "
@@ -422,8 +428,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "syn%s U{1..98}, batch %d per GPU, fdd-divide-mwkr init, replayed random "
-                                   "feasible N5 moves; one step = one l2s_step launch over the batch" % (args.shape, B),
+            "config": {"workload": workload_name(args.shape, B),
                        "shape": args.shape, "batch_per_gpu": B, "global_batch": world * B,
                        "l2": "%d independent batches stepped round-robin: per-step working set x%d > 126 MB L2"
                              % (REPLICAS, REPLICAS),
