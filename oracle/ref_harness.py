@@ -1,18 +1,19 @@
 """TEST INFRASTRUCTURE ONLY -- import the UNMODIFIED reference (zcaicaros/L2S) in the build container.
 
-This module exists to (a) validate `oracle/l2s_oracle.py` against the real reference and (b) generate
-the golden vectors committed under `tests/golden/` (see `oracle/make_golden.py`).  `/root/reference`
-does not exist on the GPU box, so nothing in `-m gpu` tests, `smoke()` or `bench.py` imports this file.
+This module exists to (a) validate `oracle/l2s_oracle.py` against the real reference, (b) generate
+the golden vectors committed under `tests/golden/` (see `oracle/make_golden.py`) and (c) run the reference as the
+CPU baseline / live checker on the GPU box from the vendored copy `baseline/_ref/` (`oracle/vendor_ref.py`;
+git-ignored, travels with gpurun).  `/root/reference` itself does not exist on the GPU box and is never read there.
 
 The reference needs packages that are absent here (torch_geometric, torch_scatter, ortools, matplotlib)
 and uses a networkx API removed in 3.x.  We install tiny in-memory stand-ins for exactly the import
 surface `env/environment.py`, `env/message_passing_evl.py` and
 `conventional_baselines_with_long-term-mem.py` touch:
 
-* `torch_geometric.nn.conv.MessagePassing.propagate` = gather + `scatter_reduce('amax')` into a zero
-  tensor (empty segment -> 0, which is what torch_scatter 2.0.6 `scatter_max` returns), honouring `flow`;
-* `torch_geometric.utils.from_networkx`, `torch_geometric.data.batch.Batch.from_data_list` for the
-  greedy baseline (edge list + node-offset concatenation);
+* `torch_geometric` = the repo's pure-torch drop-in `l2s_b200/dropin/torch_geometric` (MessagePassing.propagate =
+  gather + `scatter_reduce('amax')` into a zero tensor -- empty segment -> 0, which is what torch_scatter 2.0.6
+  `scatter_max` returns --, GINConv / GATConv / global_mean_pool for `model/actor.py`, `from_networkx`,
+  `Batch.from_data_list` for the greedy baseline);
 * `nx.from_numpy_matrix` -> `nx.from_numpy_array` (same row-major edge insertion order);
 * `sys.argv` sanitised because `parameters.py:27` parses argv at import.
 
@@ -23,7 +24,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("L2S_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VENDORED_ROOT = os.path.join(_REPO, "baseline", "_ref")      # written by oracle/vendor_ref.py; travels to the GPU box
+SHIM_ROOT = os.path.join(_REPO, "l2s_b200", "dropin")        # pure-torch torch_geometric stand-in (product drop-in)
+
+
+def _pick_root():
+    env = os.environ.get("L2S_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", VENDORED_ROOT):
+        if os.path.isfile(os.path.join(cand, "env", "environment.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available():
@@ -38,66 +54,31 @@ def _mod(name, **attrs):
 
 
 def _install_stubs():
+    """matplotlib / ortools are never called on this path: empty modules.  torch_geometric comes from the repo's
+    pure-torch drop-in (l2s_b200/dropin/torch_geometric), loaded by path so that the drop-in's own `env` package
+    (which lives next to it) never shadows the reference's."""
     import numpy as np
     import networkx as nx
-    import torch
 
-    if "torch_geometric" in sys.modules and getattr(sys.modules["torch_geometric"], "_l2s_stub", False):
-        return
+    tg = sys.modules.get("torch_geometric")
+    if tg is None or not getattr(tg, "_l2s_shim", False):
+        for k in [k for k in sys.modules if k == "torch_geometric" or k.startswith("torch_geometric.")]:
+            del sys.modules[k]
+        init = os.path.join(SHIM_ROOT, "torch_geometric", "__init__.py")
+        spec = importlib.util.spec_from_file_location("torch_geometric", init,
+                                                      submodule_search_locations=[os.path.dirname(init)])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["torch_geometric"] = mod
+        spec.loader.exec_module(mod)
 
-    class MessagePassing(torch.nn.Module):
-        def __init__(self, aggr="add", flow="source_to_target", **kw):
-            super().__init__()
-            assert aggr == "max"
-            self.aggr, self.flow = aggr, flow
-
-        def propagate(self, edge_index, x=None, size=None):
-            xs = x[0] if isinstance(x, tuple) else x
-            # source_to_target: messages x_j with j = edge_index[0] are aggregated at i = edge_index[1]
-            j, i = (0, 1) if self.flow == "source_to_target" else (1, 0)
-            src = xs.index_select(0, edge_index[j])
-            idx = edge_index[i].view(-1, *([1] * (src.dim() - 1))).expand_as(src)
-            out = torch.zeros_like(xs)
-            return out.scatter_reduce(0, idx, src, "amax", include_self=False)
-
-    def from_networkx(G):
-        edges = list(G.edges)
-        ei = torch.tensor(edges, dtype=torch.long).t().contiguous().view(2, -1)
-        return types.SimpleNamespace(edge_index=ei, num_nodes=G.number_of_nodes())
-
-    class Batch:
-        @staticmethod
-        def from_data_list(datas):
-            off, parts = 0, []
-            for d in datas:
-                parts.append(d.edge_index + off)
-                off += d.num_nodes
-            return types.SimpleNamespace(edge_index=torch.cat(parts, dim=-1))
-
-    def add_self_loops(edge_index, num_nodes=None):
-        n = int(edge_index.max()) + 1 if num_nodes is None else num_nodes
-        loop = torch.arange(n, dtype=edge_index.dtype, device=edge_index.device).repeat(2, 1)
-        return torch.cat([edge_index, loop], dim=1), None
-
-    def _unavailable(*a, **k):
-        raise RuntimeError("stubbed in oracle/ref_harness.py (policy network is out of scope)")
-
-    tg = _mod("torch_geometric", _l2s_stub=True)
-    tg.typing = _mod("torch_geometric.typing", OptPairTensor=object, Adj=object, Size=object)
-    tg.nn = _mod("torch_geometric.nn", GINConv=_unavailable, GATConv=_unavailable,
-                 global_mean_pool=_unavailable, MessagePassing=MessagePassing)
-    tg.nn.conv = _mod("torch_geometric.nn.conv", MessagePassing=MessagePassing)
-    tg.utils = _mod("torch_geometric.utils", add_self_loops=add_self_loops, sort_edge_index=_unavailable,
-                    from_networkx=from_networkx)
-    tg.data = _mod("torch_geometric.data")
-    tg.data.batch = _mod("torch_geometric.data.batch", Batch=Batch)
-
-    mpl = _mod("matplotlib")
-    mpl.pyplot = _mod("matplotlib.pyplot")
-    ort = _mod("ortools")
-    ort.sat = _mod("ortools.sat")
-    ort.sat.python = _mod("ortools.sat.python")
-    ort.sat.python.cp_model = _mod("ortools.sat.python.cp_model", CpSolverSolutionCallback=object)
+    if "matplotlib" not in sys.modules:
+        mpl = _mod("matplotlib")
+        mpl.pyplot = _mod("matplotlib.pyplot")
+    if "ortools" not in sys.modules:
+        ort = _mod("ortools")
+        ort.sat = _mod("ortools.sat")
+        ort.sat.python = _mod("ortools.sat.python")
+        ort.sat.python.cp_model = _mod("ortools.sat.python.cp_model", CpSolverSolutionCallback=object)
 
     if not hasattr(nx, "from_numpy_matrix"):
         def from_numpy_matrix(A, parallel_edges=False, create_using=None):
@@ -127,6 +108,7 @@ def load():
         import env.message_passing_evl as ref_evl
         import env.generateJSP as ref_gen
         import env.permissible_LS as ref_pls
+        import model.actor as ref_actor
         spec = importlib.util.spec_from_file_location(
             "ref_conventional_baselines",
             os.path.join(REFERENCE_ROOT, "conventional_baselines_with_long-term-mem.py"))
@@ -138,5 +120,6 @@ def load():
     _loaded.update(JsspN5=ref_env.JsspN5, BatchGraph=ref_env.BatchGraph, Evaluator=ref_evl.Evaluator,
                    CPM_batch_G=ref_evl.CPM_batch_G, uni_instance_gen=ref_gen.uni_instance_gen,
                    Greedy_baselines=ref_bl.Greedy_baselines, permissibleLeftShift=ref_pls.permissibleLeftShift,
-                   env_module=ref_env, evl_module=ref_evl, baselines_module=ref_bl)
+                   env_module=ref_env, evl_module=ref_evl, baselines_module=ref_bl, Actor=ref_actor.Actor,
+                   actor_module=ref_actor, root=REFERENCE_ROOT)
     return types.SimpleNamespace(**_loaded)
