@@ -74,6 +74,9 @@ int l2s_destroy(l2s_handle h);
 int l2s_pmax(l2s_handle h);
 int64_t l2s_edges_mc_per_instance(l2s_handle h); /* n_m*(n_j-1) */
 int64_t l2s_itr(l2s_handle h);                   /* steps applied since the last reset (JsspN5.itr)      */
+/* Set the step counter (JsspN5.itr): callers that advance the search outside l2s_step / l2s_run -- replaying a
+ * captured CUDA graph -- keep the handle's counter (which keys the RANDOM policy's RNG) in step with theirs. */
+int l2s_set_itr(l2s_handle h, int64_t itr);
 int l2s_launch_info(l2s_handle h, int* warps_per_cta_step, int* smem_per_instance, int* warps_per_cta_run);
 
 /* Durations and 1-based machine ids, both [batch, n_j*n_m] int32 (the reference's instances[:,0], [:,1]).

@@ -9,6 +9,6 @@ resolve to this package.
 """
 from ._capi import L2SError, lib, lib_path  # noqa: F401
 from .environment import BatchGraph, JsspN5  # noqa: F401
-from .message_passing_evl import Evaluator  # noqa: F401
+from .message_passing_evl import CPM_batch_G, Evaluator  # noqa: F401
 
-__all__ = ["JsspN5", "BatchGraph", "Evaluator", "L2SError", "lib", "lib_path"]
+__all__ = ["JsspN5", "BatchGraph", "Evaluator", "CPM_batch_G", "L2SError", "lib", "lib_path"]

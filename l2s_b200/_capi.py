@@ -49,6 +49,7 @@ PROTOTYPES = {
     "l2s_pmax": (C.c_int, [C.c_void_p]),
     "l2s_edges_mc_per_instance": (C.c_int64, [C.c_void_p]),
     "l2s_itr": (C.c_int64, [C.c_void_p]),
+    "l2s_set_itr": (C.c_int, [C.c_void_p, C.c_int64]),
     "l2s_launch_info": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_i32p]),
     "l2s_load_instances": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "l2s_set_solution": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

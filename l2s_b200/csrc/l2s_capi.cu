@@ -313,6 +313,11 @@ int l2s_destroy(l2s_handle h) {
 int l2s_pmax(l2s_handle h) { return h ? h->pmax : L2S_ERR_INVALID_ARG; }
 int64_t l2s_edges_mc_per_instance(l2s_handle h) { return h ? h->L.e_mc : L2S_ERR_INVALID_ARG; }
 int64_t l2s_itr(l2s_handle h) { return h ? h->itr : L2S_ERR_INVALID_ARG; }
+int l2s_set_itr(l2s_handle h, int64_t itr) {
+  if (!h || itr < 0) return L2S_ERR_INVALID_ARG;
+  h->itr = itr;
+  return L2S_OK;
+}
 
 int l2s_launch_info(l2s_handle h, int* warps_per_cta_step, int* smem_per_instance, int* warps_per_cta_run) {
   if (!h) return L2S_ERR_INVALID_ARG;

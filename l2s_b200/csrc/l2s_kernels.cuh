@@ -170,6 +170,9 @@ __global__ void build_initial_kernel(Layout L, InitLayout IL, State st, int B, i
       const int oj = __shfl_xor_sync(kFull, bj, o);
       if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
     }
+    // malformed input that load_kernel has flagged (NaN priorities from an all-zero job, a job that repeats a
+    // machine) must not turn into out-of-bounds accesses here, whatever order the host polls errors in
+    if (bj >= n_j) break;
     const int j = bj;
     const int kpos = nxt[j];
     const int v = j * n_m + kpos + 1;           // node id
@@ -177,7 +180,7 @@ __global__ void build_initial_kernel(Layout L, InitLayout IL, State st, int B, i
     const int m = (int)mch[v - 1] - 1;
     int32_t* rs = starts + m * n_j;
     uint16_t* ro = ops + m * n_j;
-    const int c = cnt[m];
+    const int c = min(cnt[m], n_j - 1);
     const int job_rdy = rdy[j];
     const int mch_rdy = c ? rs[c - 1] + (durw[ro[c - 1]] & kDurMask) : 0;
     // first placed op that starts after job_rdy (rows are sorted by start time)
@@ -246,7 +249,8 @@ __global__ void build_initial_kernel(Layout L, InitLayout IL, State st, int B, i
   uint32_t* walk = st.walk + (size_t)b * L.walk_stride;
   for (int m = 0; m < n_m; ++m)
     for (int k = lane; k < n_j; k += 32) {
-      const int idx = m * n_j + k, v = ops[idx];
+      const int idx = m * n_j + k;
+      const int v = min(max((int)ops[idx], 1), L.n);   // (garbage only for instances load_kernel rejected)
       walk[idx] = make_walk(v, durw[v], false, k == n_j - 1);
     }
   for (int i = L.n + lane; i < L.walk_stride; i += 32) walk[i] = 0;

@@ -9,6 +9,7 @@ hands them to the policy as Python lists (model/actor.py:216-226).
 There is no CPU path: `device` must be a CUDA device and the CUDA library must be built.
 """
 import ctypes as C
+from collections.abc import Sequence
 
 import numpy as np
 import torch
@@ -31,6 +32,77 @@ class BatchGraph:
 
     def clean(self):
         self.x = self.edge_index_pc = self.edge_index_mc = self.batch = None
+
+
+class MoveLists(Sequence):
+    """`feasible_actions` of one step: behaves like the reference's `list[B] of list[P_i] of [a0, a1]`
+    (env/environment.py:411-423; an instance without moves holds `[[0, 0]]`), but is a lazy view of a snapshot of
+    the per-instance host records the step kernel wrote: nothing is allocated per instance until someone asks.
+    The reference policy needs `len(fa)`, `len(fa[i])`, `fa[i][j][0|1]` (model/actor.py:216-222); tests compare it with
+    plain lists (`==`); `arrays()` hands the same data out as numpy for consumers that want no Python lists at all
+    (l2s_b200.policy.Actor.forward).  Building ~10 small lists per instance cost ~4 ms per 8192-instance step."""
+    __slots__ = ("_rec", "_lists")
+
+    def __init__(self, records):
+        self._rec = records              # [B, 4 + pmax] uint32, private copy
+        self._lists = None
+
+    def __len__(self):
+        return self._rec.shape[0]
+
+    def _row(self, b):
+        row = self._rec[b]
+        c = int(row[0]) & 0xffff
+        if c == 0:
+            return [[0, 0]]
+        w = row[_capi.REC_HEADER_WORDS:_capi.REC_HEADER_WORDS + c]
+        return np.stack([w & 0xffff, w >> 16], axis=1).tolist()
+
+    def tolist(self):
+        """The fully materialised nested list (built once, at C speed when the CPython glue is available)."""
+        if self._lists is None:
+            glue = _capi.pylists()
+            if glue is not None:
+                self._lists = glue.l2s_build_move_lists(self._rec.ctypes.data, self._rec.shape[1], self._rec.shape[0])
+            else:
+                self._lists = [self._row(b) for b in range(len(self))]
+        return self._lists
+
+    def __getitem__(self, b):
+        if self._lists is not None or isinstance(b, slice):
+            return self.tolist()[b]
+        n = self._rec.shape[0]
+        if b < -n or b >= n:
+            raise IndexError("instance index out of range")
+        return self._row(b)
+
+    def __iter__(self):
+        return iter(self.tolist())
+
+    def __eq__(self, other):
+        if isinstance(other, MoveLists):
+            other = other.tolist()
+        return self.tolist() == other
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return "MoveLists(%r)" % (self.tolist(),)
+
+    def counts(self):
+        """int32 [B]: number of feasible pairs per instance (0 where the reference returns [[0, 0]])."""
+        return (self._rec[:, 0] & 0xffff).astype(np.int32)
+
+    def arrays(self):
+        """(pairs int32 [B, pmax, 2], npairs int32 [B]); rows are valid up to npairs[b], zero beyond."""
+        cnt = self.counts()
+        w = self._rec[:, _capi.REC_HEADER_WORDS:]
+        valid = np.arange(w.shape[1])[None, :] < cnt[:, None]
+        w = np.where(valid, w, 0)
+        return np.stack([w & 0xffff, w >> 16], axis=2).astype(np.int32), cnt
 
 
 def _stream_ptr(device):
@@ -92,6 +164,8 @@ class JsspN5:
         self._key = None
         self._device = None
         self._const = None
+        self._h_rec = self._h_actions = self._h_actions_ptr = None
+        self._fa = self._flag = None
         self._lib = _capi.lib()
 
     # -- handle management -----------------------------------------------------------------------------
@@ -102,9 +176,17 @@ class JsspN5:
             pass
 
     def close(self):
+        """Destroy the handle.  The numpy views of its pinned host buffers die with it."""
         if self._h is not None:
             self._lib.l2s_destroy(self._h)
             self._h = None
+        self._key = None
+        self._h_rec = self._h_actions = self._h_actions_ptr = None
+        self._fa = self._flag = None
+
+    def _live(self, what):
+        if self._h is None:
+            raise RuntimeError("JsspN5.%s: no live environment -- call reset() first (or the handle was closed)" % what)
 
     def _ensure_handle(self, B, device):
         device = torch.device(device)
@@ -155,6 +237,7 @@ class JsspN5:
         dur, mch = di[:, 0].contiguous(), di[:, 1].contiguous()
         _capi.check(self._lib.l2s_load_instances(self._h, _ptr(dur), _ptr(mch), self.instance_offset, stream),
                     "l2s_load_instances")
+        self._poll("reset")      # malformed instances are reported before anything is built from them
         if init_solutions is not None:
             sol = torch.from_numpy(np.ascontiguousarray(np.asarray(init_solutions)).astype(np.int32)).to(device)
             assert sol.shape == (B, self.n_mch, self.n_job)
@@ -178,7 +261,6 @@ class JsspN5:
             sol = self.solutions().cpu().numpy()
             self.pmax *= 2
             self.close()
-            self._key = None
             return self.reset(instances, init_type, device, plot=plot, init_solutions=sol)
         return state, fa, done
 
@@ -187,6 +269,7 @@ class JsspN5:
         like env/environment.py:356-387."""
         if self.reward_type not in _capi.REWARD:
             raise ValueError('reward type must be "yaoxin" or "consecutive".')
+        self._live("step")
         glue = _capi.pylists()
         if glue is not None and not isinstance(actions, np.ndarray):
             if glue.l2s_parse_actions(actions, self._h_actions.ctypes.data, self._key[0]) != 0:
@@ -213,6 +296,53 @@ class JsspN5:
         _capi.check(self._lib.l2s_export_state(self._h, None, None, None, None, _ptr(tabu), None, None, None,
                                                _stream_ptr(self._device)), "l2s_export_state")
         return [[] if (a == 0 and b == 0) else [[a, b]] for a, b in tabu.cpu().tolist()]
+
+    def _nx_graphs(self):
+        """networkx views of the current solutions, built on demand (the reference keeps them as its primary state,
+        env/environment.py:262-268; here the state lives on the GPU and only the baselines scripts read these,
+        conventional_baselines_with_long-term-mem.py:100).  Arc weights = duration of the source node; the in-arcs
+        of every node are inserted in the order networkx's `G.pred[v]` has in the reference after the same moves
+        (job predecessor first iff the tie-break history bit is set or its id is smaller), so `nx.dag_longest_path`
+        on these graphs returns the reference's critical paths."""
+        import networkx as nx
+        B, n, n_m, n_j = self._key[0], self.n_oprs, self.n_mch, self.n_job
+        mseq = self.solutions().cpu().numpy()
+        jf = self.export_state()["jobfirst"].cpu().numpy()
+        dur = np.asarray(self.instances)[:, 0].reshape(B, -1)
+        full, mc = [], []
+        for b in range(B):
+            mpred = np.zeros(n + 2, dtype=np.int64)
+            mpred[mseq[b][:, 1:].reshape(-1)] = mseq[b][:, :-1].reshape(-1)
+            d = np.concatenate([[0], dur[b], [0]])
+            G = nx.DiGraph()
+            G.add_nodes_from(range(n + 2))
+            Gm = nx.DiGraph()
+            Gm.add_nodes_from(range(n + 2))
+            for v in range(1, n + 1):
+                jp = v - 1 if (v - 1) % n_m != 0 else 0
+                mp = int(mpred[v])
+                preds = [u for u in ([jp, mp] if (jf[b, v] or (jp and jp < mp)) else [mp, jp]) if u]
+                if not jp:
+                    preds.append(0)                       # S -> first operation of a job is (re-)added last (:264)
+                for u in preds:
+                    G.add_edge(u, v, weight=int(d[u]))
+                if mp:
+                    Gm.add_edge(mp, v, weight=1)
+            for j in range(n_j):
+                G.add_edge(j * n_m + n_m, n + 1, weight=int(d[j * n_m + n_m]))
+            full.append(G)
+            mc.append(Gm)
+        return full, mc
+
+    @property
+    def current_graphs(self):
+        """list[B] of nx.DiGraph: full disjunctive graphs (lazily built, see `_nx_graphs`)."""
+        return self._nx_graphs()[0] if self._h is not None else None
+
+    @property
+    def sub_graphs_mc(self):
+        """list[B] of nx.DiGraph: machine arcs only (lazily built)."""
+        return self._nx_graphs()[1] if self._h is not None else None
 
     def solutions(self):
         """Current machine orders [B, n_m, n_j] int32 (device tensor) -- extension."""
@@ -251,6 +381,7 @@ class JsspN5:
         Returns (state, reward [B,1], pairs int32 [B,pmax,2], npairs int32 [B], done bool [B,1])."""
         if self.reward_type not in _capi.REWARD:
             raise ValueError('reward type must be "yaoxin" or "consecutive".')
+        self._live("step_device")
         assert actions.dtype == torch.int32 and actions.is_cuda and actions.shape == (self._key[0], 2)
         res = self._launch_device(actions.contiguous(), is_reset=False, out=out)
         self.itr = self.itr + 1
@@ -297,6 +428,7 @@ class JsspN5:
         """K = `steps` fused steps in ONE launch with an on-device policy ('replay' with tape [B,K,2],
         'random', 'greedy').  Returns (incumbents at log_steps [len(log_steps), B] float32 device tensor,
         actions taken [B,K,2] int32 or None).  Call `observe()` afterwards for the policy inputs."""
+        self._live("run")
         B, dev = self._key[0], self._device
         tape_t = None
         if policy == 'replay':
@@ -315,6 +447,7 @@ class JsspN5:
     def observe(self):
         """Re-evaluate without moving (a launch without actions changes neither the incumbent nor the step
         counter): refreshes current/incumbent tensors and returns (state, feasible_actions, done)."""
+        self._live("observe")
         state, _, fa, done = self._launch(None, self._device, is_reset=False)
         return state, fa, done
 
@@ -372,19 +505,7 @@ class JsspN5:
             _raise_status(int(status[b]), b, "step")
         self.current_objs = ms
         self.incumbent_objs = inc
-        glue = _capi.pylists()
-        if glue is not None:
-            fa = glue.l2s_build_move_lists(rec.ctypes.data, rec.shape[1], B)
-        else:
-            npairs = (head & 0xffff).astype(np.int64)
-            words = rec[:, _capi.REC_HEADER_WORDS:]
-            sel = words[np.arange(words.shape[1])[None, :] < npairs[:, None]]
-            flat = np.stack([sel & 0xffff, sel >> 16], axis=1).tolist()
-            ends = np.cumsum(npairs).tolist()
-            fa, s = [], 0
-            for e in ends:
-                fa.append(flat[s:e] if e > s else [[0, 0]])
-                s = e
+        fa = MoveLists(rec.copy())       # the pinned records are overwritten by the next step: snapshot (~1 MB memcpy)
         self._fa = fa
         self._flag = ~done
         return (x, self._const[0], emc, self._const[1]), reward, fa, done

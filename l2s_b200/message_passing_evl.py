@@ -70,3 +70,38 @@ class Evaluator:
             if flag < 0:
                 raise L2SError(flag, "Evaluator.forward")
         return est, lst, ms
+
+
+_cpm_evaluator = None
+
+
+def CPM_batch_G(Gs, dev):
+    """Drop-in for the reference's networkx critical-path evaluator (env/message_passing_evl.py:275-287):
+    `Gs` is a list of `nx.DiGraph` disjunctive graphs (nodes 0..n+1, S = 0, T = n+1, every arc weighted with the
+    duration of its source node, as `JsspN5._init_solver` builds them, env/environment.py:262-265); returns
+    `(est [N,1], lst [N,1], makespan [B,1])` float32 on `dev`.  The reference walks each graph in topological
+    order in Python; here the arcs are flattened into one COO list and evaluated by the same CUDA kernels as
+    `Evaluator.forward` (the two evaluators of the reference agree, `:367-371`, so the numbers are identical).
+    `n_j` is read off the graph (out-degree of S), `n_m = n / n_j`; all graphs of a batch must share the shape."""
+    global _cpm_evaluator
+    import numpy as np
+    device = torch.device(dev)
+    if device.type != 'cuda':
+        raise RuntimeError("l2s_b200.CPM_batch_G runs on CUDA devices only (no CPU fallback); got dev=%r" % (dev,))
+    n1 = Gs[0].number_of_nodes()
+    n_j = Gs[0].out_degree(0)
+    n_m = (n1 - 2) // n_j
+    eis, durs = [], []
+    for k, G in enumerate(Gs):
+        if G.number_of_nodes() != n1 or G.out_degree(0) != n_j:
+            raise ValueError("all graphs of a batch must have the same n_j x n_m shape")
+        e = np.fromiter((v for u, w, d in G.edges(data='weight') for v in (u, w, d)), dtype=np.int64).reshape(-1, 3)
+        dur = np.zeros(n1, dtype=np.int64)
+        dur[e[:, 0]] = e[:, 2]                      # every arc carries its source's duration
+        eis.append(e[:, :2].T + k * n1)
+        durs.append(dur)
+    ei = torch.from_numpy(np.ascontiguousarray(np.concatenate(eis, axis=1))).to(device)
+    dur = torch.from_numpy(np.concatenate(durs)).reshape(-1, 1).to(device)
+    if _cpm_evaluator is None:
+        _cpm_evaluator = Evaluator()
+    return _cpm_evaluator.forward(ei, dur, n_j, n_m)

@@ -25,6 +25,67 @@ import torch.nn.functional as F
 from torch.distributions.categorical import Categorical
 
 
+class _AllReduceSum(torch.autograd.Function):
+    """Sum over ranks, differentiable: the gradient of a sum over ranks is the sum of the gradients."""
+
+    @staticmethod
+    def forward(ctx, t, group):
+        import torch.distributed as dist
+        ctx.group = group
+        out = t.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+class ShardedBatchNorm1d(nn.BatchNorm1d):
+    """BatchNorm1d whose TRAINING-mode statistics are taken over the rows of all ranks (one all-reduce of
+    [sum, sum of squares, count] in float64 per forward, one more in backward).  The reference never calls
+    `.eval()`, so its GIN layers normalise every forward with the statistics of the whole rollout
+    batch (model/actor.py:74,88); with the batch sharded over ranks, per-rank statistics would change the logits.
+    Same parameters / buffers / state-dict keys as BatchNorm1d; without an initialised process group (or with one
+    rank) it IS BatchNorm1d.  Works with any backend (nccl on GPUs, gloo in the CPU tests)."""
+    group = None
+
+    def forward(self, x):
+        import torch.distributed as dist
+        if not (self.training and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return super().forward(x)
+        xd = x.double()
+        stats = torch.cat([xd.sum(0), (xd * xd).sum(0), xd.new_full((1,), float(x.shape[0]))])
+        stats = _AllReduceSum.apply(stats, self.group)
+        c = x.shape[1]
+        cnt = stats[2 * c]
+        mean = stats[:c] / cnt
+        var = (stats[c:2 * c] / cnt - mean * mean).clamp(min=0.0)          # biased, like BatchNorm's normaliser
+        if self.track_running_stats:
+            with torch.no_grad():
+                self.num_batches_tracked += 1
+                m = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
+                self.running_mean.mul_(1 - m).add_(mean.to(self.running_mean.dtype), alpha=m)
+                self.running_var.mul_(1 - m).add_((var * cnt / (cnt - 1).clamp(min=1)).to(self.running_var.dtype), alpha=m)
+        y = (xd - mean) * torch.rsqrt(var + self.eps)
+        y = y.to(x.dtype)
+        if self.affine:
+            y = y * self.weight + self.bias
+        return y
+
+
+def shard_batchnorm(module, group=None):
+    """Switch every BatchNorm1d of `module` to cross-rank statistics (in place; state dict unchanged)."""
+    for m in module.modules():
+        if type(m) is nn.BatchNorm1d:
+            m.__class__ = ShardedBatchNorm1d
+            m.group = group
+    return module
+
+
 def _with_self_loops(edge_index, num_nodes):
     loop = torch.arange(num_nodes, dtype=edge_index.dtype, device=edge_index.device)
     return torch.cat([edge_index, loop.unsqueeze(0).repeat(2, 1)], dim=1)
@@ -203,14 +264,18 @@ class Actor(nn.Module):
         the environment returns; returns (list of [a0, a1], log_prob [B, 1])."""
         dev = batch_states.x.device
         B = len(feasible_actions)
-        P = max(len(f) for f in feasible_actions)
-        pairs = np.zeros((B, P, 2), dtype=np.int32)
-        cnt = np.zeros(B, dtype=np.int32)
-        for i, f in enumerate(feasible_actions):
-            if len(f) == 1 and f[0][0] == 0 and f[0][1] == 0:
-                continue
-            cnt[i] = len(f)
-            pairs[i, :len(f)] = np.asarray(f, dtype=np.int32)
+        if hasattr(feasible_actions, "arrays"):          # l2s_b200.environment.MoveLists: no Python lists at all
+            pairs, cnt = feasible_actions.arrays()
+            pairs = np.ascontiguousarray(pairs[:, :max(1, int(cnt.max()))])
+        else:
+            P = max(len(f) for f in feasible_actions)
+            pairs = np.zeros((B, P, 2), dtype=np.int32)
+            cnt = np.zeros(B, dtype=np.int32)
+            for i, f in enumerate(feasible_actions):
+                if len(f) == 1 and f[0][0] == 0 and f[0][1] == 0:
+                    continue
+                cnt[i] = len(f)
+                pairs[i, :len(f)] = np.asarray(f, dtype=np.int32)
         act, log_prob = self.forward_device(batch_states.x, batch_states.edge_index_pc, batch_states.edge_index_mc,
                                             batch_states.batch, torch.from_numpy(pairs).to(dev),
                                             torch.from_numpy(cnt).to(dev))

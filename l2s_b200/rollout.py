@@ -12,13 +12,18 @@ class GraphedRollout:
         self.env, self.policy, self.greedy = env, policy, greedy
         self.graph = None
         self.buf = None
+        self._ident = None        # (handle address, pmax) the buffers and the captured graph belong to
 
     def reset(self, instances, init_type, device, init_solutions=None):
         env = self.env
         state, pairs, npairs, done = env.reset_device(instances, init_type, device, init_solutions=init_solutions)
-        if self.buf is None or self.buf["x"].shape != state[0].shape:
+        # the captured launch holds the handle's device pointers and its pmax: a new handle (different batch, a
+        # regrown pair list after PAIR_OVERFLOW, close + reset) invalidates both the graph and the buffers
+        ident = (env._h.value, env.pmax, tuple(state[0].shape))
+        if self.buf is None or self._ident != ident:
             self.buf = env.device_buffers()
             self.graph = None
+            self._ident = ident
         b = self.buf
         b["x"].copy_(state[0]); b["emc"].copy_(state[2]); b["pairs"].copy_(pairs); b["npairs"].copy_(npairs)
         b["done"].copy_(done); b["ms"].copy_(env.current_objs); b["inc"].copy_(env.incumbent_objs)
@@ -45,7 +50,14 @@ class GraphedRollout:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self._one_step()
         self.env.itr -= 1        # the captured call only recorded the work; it did not advance the search
+        self._sync_itr()
         return self
+
+    def _sync_itr(self):
+        """Graph replays do not pass through l2s_step, so the C handle's step counter (the RANDOM policy's RNG key)
+        is set from the Python-side one."""
+        from . import _capi
+        _capi.check(_capi.lib().l2s_set_itr(self.env._h, int(self.env.itr)), "l2s_set_itr")
 
     def run(self, until_itr, log_steps=()):
         """Replay until env.itr == until_itr.  Returns {step: incumbents [B] (device tensor clone)}."""
@@ -57,5 +69,6 @@ class GraphedRollout:
             env.itr += 1
             if env.itr in log_steps:
                 logs[env.itr] = env.incumbent_objs.reshape(-1).clone()
+        self._sync_itr()
         env.check_errors()
         return logs

@@ -68,3 +68,90 @@ def test_two_rank_sharded_search_equals_unsharded():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out.get("same_cur") and out.get("same_inc") and out.get("ok_grad"), dict(out)
+
+
+def _policy_state(B, n_j, n_m, seed):
+    """Synthetic policy inputs of B equal-sized graphs (the policy is pure torch, so this runs on CPU)."""
+    rng = np.random.RandomState(seed)
+    n1 = n_j * n_m + 2
+    x = torch.from_numpy(rng.rand(B * n1, 3).astype(np.float32))
+    pcs, mcs, pairs = [], [], []
+    for b in range(B):
+        u = np.arange(1, n_j * n_m + 1)
+        v = np.where(u % n_m != 0, u + 1, n1 - 1)
+        first = np.arange(n_j) * n_m + 1
+        pcs.append(np.stack([np.concatenate([np.zeros(n_j, np.int64), u]), np.concatenate([first, v])]) + b * n1)
+        perm = rng.permutation(u)[:n_m * (n_j - 1) + 1]
+        mcs.append(np.stack([perm[:-1], perm[1:]]) + b * n1)
+        pairs.append(rng.randint(1, n_j * n_m, size=(4, 2)))
+    pc = torch.from_numpy(np.concatenate(pcs, axis=1)).long()
+    mc = torch.from_numpy(np.concatenate(mcs, axis=1)).long()
+    batch = torch.arange(B).repeat_interleave(n1)
+    return x, pc, mc, batch, torch.from_numpy(np.stack(pairs)).int(), torch.full((B,), 4, dtype=torch.int32)
+
+
+def _slice_state(st, lo, hi, n1, e_pc, e_mc):
+    x, pc, mc, batch, pairs, npairs = st
+    return (x[lo * n1:hi * n1], pc[:, lo * e_pc:hi * e_pc] - lo * n1, mc[:, lo * e_mc:hi * e_mc] - lo * n1,
+            batch[lo * n1:hi * n1] - lo, pairs[lo:hi], npairs[lo:hi])
+
+
+def _bn_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from l2s_b200.policy import Actor, shard_batchnorm
+    from l2s_b200.sharding import allreduce_mean_gradients
+    n_j, n_m, B = 5, 4, 6
+    n1, e_pc, e_mc = n_j * n_m + 2, n_j * (n_m + 1), n_m * (n_j - 1)
+    st = _policy_state(B, n_j, n_m, seed=4)
+    torch.manual_seed(7)
+    ref = Actor(3, 32, embedding_l=2, policy_l=2, embedding_type='gin+dghan', heads=1, dropout=0.0)
+    sharded = Actor(3, 32, embedding_l=2, policy_l=2, embedding_type='gin+dghan', heads=1, dropout=0.0)
+    sharded.load_state_dict(ref.state_dict())
+    shard_batchnorm(sharded)
+
+    def loss_of(model, s):
+        h = model.node_features(s[0], s[1], s[2], s[4].shape[0])
+        idx = s[4].long()
+        ha = torch.gather(h, 1, idx[:, :, 0:1].expand(-1, -1, h.shape[-1]))
+        hb = torch.gather(h, 1, idx[:, :, 1:2].expand(-1, -1, h.shape[-1]))
+        logp = torch.log_softmax((ha * hb).sum(-1), dim=1)
+        return h, -logp[:, 0].mean()                  # batch-mean loss, like the REINFORCE learner
+
+    # unsharded run (every rank computes it locally: plain BatchNorm over all B graphs)
+    h_full, loss_full = loss_of(ref, st)
+    loss_full.backward()
+    # sharded run: rank r holds B/world graphs, BatchNorm statistics all-reduced, gradients averaged
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    h_loc, loss_loc = loss_of(sharded, _slice_state(st, lo, hi, n1, e_pc, e_mc))
+    loss_loc.backward()
+    allreduce_mean_gradients(list(sharded.parameters()))
+    err_h = float((h_loc - h_full[lo:hi]).detach().abs().max())
+    # relative to the largest gradient entry of the model (a Linear bias in front of a BatchNorm has a gradient that
+    # is zero up to rounding noise, so a per-tensor relative error would compare noise with noise)
+    gmax = max(float(b.grad.abs().max()) for b in ref.parameters() if b.grad is not None)
+    err_g = max(float((a.grad - b.grad).abs().max()) / gmax
+                for a, b in zip(sharded.parameters(), ref.parameters()) if b.grad is not None)
+    bufs = max(float((dict(sharded.named_buffers())[k] - v).abs().max()) for k, v in ref.named_buffers()
+               if v.dtype.is_floating_point)
+    # control: per-rank statistics (plain BatchNorm on the slice) do NOT reproduce the unsharded embeddings
+    plain = Actor(3, 32, embedding_l=2, policy_l=2, embedding_type='gin+dghan', heads=1, dropout=0.0)
+    plain.load_state_dict(ref.state_dict())
+    h_plain, _ = loss_of(plain, _slice_state(st, lo, hi, n1, e_pc, e_mc))
+    out["r%d" % rank] = (err_h, err_g, bufs, float((h_plain - h_full[lo:hi]).detach().abs().max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_batchnorm_reproduces_unsharded_embeddings_and_gradients():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bn_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in range(2):
+        err_h, err_g, bufs, err_plain = out["r%d" % r]
+        assert err_h < 1e-5, "embeddings differ from the unsharded run: %g" % err_h
+        assert err_g < 1e-4, "all-reduced gradients differ from the unsharded run: %g (relative)" % err_g
+        assert bufs < 1e-5, "BatchNorm running statistics differ: %g" % bufs
+        assert err_plain > 1e-3, "control failed: per-rank statistics should change the embeddings"
