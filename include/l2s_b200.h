@@ -134,7 +134,8 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
                   int32_t* status_host, void* stream);
 
 /* Host result records of l2s_step_host: `records` is [batch][stride_words] uint32 in pinned host memory owned by
- * the handle, stride_words = L2S_REC_HEADER_WORDS + pmax.  Record of instance b:
+ * the handle, stride_words = L2S_REC_HEADER_WORDS + pmax rounded up to a multiple of 16 (every record starts on a
+ * 64-byte line).  Record of instance b:
  *   word 0      npairs (bits 0-15) | done (bit 16) | per-instance l2s_status as int8 (bits 24-31)
  *   word 1..3   makespan, reward, incumbent as float32 bit patterns
  *   word 4+i    feasible pair i (i < npairs) in critical-path order: a0 | a1 << 16 (node ids fit 16 bits);
@@ -146,6 +147,16 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
 #define L2S_REC_DONE(w0) (((w0) >> 16) & 1u)
 #define L2S_REC_STATUS(w0) ((int)(int8_t)((w0) >> 24))
 int l2s_host_records(l2s_handle h, const uint32_t** records, int* stride_words, int32_t** actions);
+
+/* Tuning knobs of a handle (all have measured defaults; also settable through the environment at l2s_create):
+ *   "host_wait_flag"       l2s_step_host waits on a polled stream-ordered flag instead of cudaStreamSynchronize
+ *   "host_zero_copy"       the kernel reads host actions in place (1) / they are copied H2D first (0)
+ *   "host_action_prefetch" with zero copy: a small kernel pulls the action block with 16-byte coalesced reads
+ *   "host_records_direct"  the kernel writes the records straight into host memory (1) / device staging + D2H (0)
+ *   "host_record_lines"    records are written as whole 64-byte lines
+ *   "incremental"          large instances: resume the sweeps from the evaluation kept in HBM
+ * Returns L2S_ERR_INVALID_ARG for an unknown name. */
+int l2s_set_option(l2s_handle h, const char* name, int value);
 
 /* K fused steps in ONE launch with an on-device policy; the search state never leaves shared memory.
  *   REPLAY: tape [batch, K, 2] int32 actions.

@@ -56,9 +56,9 @@ Layout make_layout(int n_j, int n_m, bool stage_durw = false, int pmax = 0) {
   // host record staging (4 + pmax words): the critical-predecessor array is dead by then; tiny instances get
   // their own region
   L.off_rec = L.off_crit;
-  if ((4 + pmax) * 4 > L.node_stride * 2) {
+  if (ru(4 + pmax, 16) * 4 > L.node_stride * 2) {
     L.off_rec = off;
-    off += ru((4 + pmax) * 4, 16);
+    off += ru(4 + pmax, 16) * 4;
   }
   L.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   L.bytes = ru(off, 16);
@@ -115,6 +115,7 @@ struct l2s_handle_s {
   long long itr;
   int warps_step, warps_run, warps_init;
   int cta_warps;   // > 0: large instances -> step_kernel_cta with this many warps per instance
+  int incremental; // CTA kernel: keep fin / q of the last evaluation in HBM and resume the sweeps from them
   size_t run_stride, run_stride_greedy;
   int run_off_where, run_off_plist, run_off_walk2;
   int warps_run_greedy;
@@ -127,6 +128,9 @@ struct l2s_handle_s {
   uint32_t* h_rec_dev;         // device-side address of h_rec
   uint32_t* d_rec;             // device staging, only for rec_direct == 0
   size_t rec_bytes;
+  int rec_stride;              // words per record: 4 + pmax rounded up to a multiple of 16 (64-byte lines)
+  int rec_lines;               // 1: the kernel writes whole 64-byte lines (padding words are stale)
+  int act_prefetch;            // 1: a small kernel copies the host actions to the device with 16-byte coalesced reads
   // divisors already verified for the FMA division (x features)
   float div_c[2], div_r[2];
   int div_mode[2];
@@ -134,7 +138,33 @@ struct l2s_handle_s {
   // L2S_HOST_RECORDS=0 writes the records to device memory and copies them back with one bulk D2H)
   int zero_copy;
   int rec_direct;
+  // completion of a host-driven step: 0 = cudaStreamSynchronize; 1 = a stream-ordered 32-bit write into mapped pinned
+  // host memory (cuStreamWriteValue32, fenced behind the kernel's own host writes) that the calling thread polls
+  int wait_flag;
+  int host_debug;              // experiments (L2S_HOST_DEBUG): 1 = the kernel writes no host records, 2 = actions are
+                               // taken from device memory without any transfer (both make the results meaningless)
+  uint32_t* h_flag;            // pinned + mapped
+  uint32_t* h_flag_dev;
+  uint32_t flag_epoch;
 };
+
+// cuStreamWriteValue32 through the runtime's driver entry-point lookup (no link-time dependency on libcuda)
+typedef int (*l2s_write32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static l2s_write32_fn resolve_write32() {
+  static l2s_write32_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = (l2s_write32_fn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
 
 extern "C" {
 
@@ -245,6 +275,15 @@ static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int 
   CU(cudaMalloc(&st.cur, B * 4));
   CU(cudaMalloc(&st.inc, B * 4));
   CU(cudaMalloc(&st.err, 4));
+  // incremental re-evaluation behind the step API: only the CTA kernel (large instances, where sweep levels are a
+  // third to a half of a step) keeps the last evaluation; L2S_INCREMENTAL=0 turns it off (experiments, tests)
+  h->incremental = h->cta_warps > 0;
+  if (const char* e = getenv("L2S_INCREMENTAL")) h->incremental = h->incremental && atoi(e) != 0;
+  if (h->incremental) {
+    CU(cudaMalloc(&st.fq, B * 2 * (size_t)L.n1p * 4));
+    CU(cudaMalloc(&st.evalid, B * 4));
+    CU(cudaMemset(st.evalid, 0, B * 4));
+  }
   {
     int32_t* page = nullptr;
     CU(cudaMalloc(&page, (size_t)2 * L.n1p * 4));
@@ -262,13 +301,14 @@ static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int 
   // host-step staging.  Measured on B200 (20x15, 8192 instances per step): records written by the kernel straight
   // into mapped host memory (one coalesced store of 16 + 4*npairs bytes per instance, overlapping the rest of the
   // launch) 57 us per step; packed SoA block + one bulk D2H 84 us; scattered 4-byte zero-copy stores: slower still.
-  h->rec_bytes = B * (size_t)(4 + pmax) * 4;
+  h->rec_stride = ru(L2S_REC_HEADER_WORDS + pmax, 16);     // whole 64-byte lines per record
+  h->rec_bytes = B * (size_t)h->rec_stride * 4;
   CU(cudaHostAlloc((void**)&h->h_rec, h->rec_bytes, cudaHostAllocMapped));
   memset(h->h_rec, 0, h->rec_bytes);
   CU(cudaHostGetDevicePointer((void**)&h->h_rec_dev, h->h_rec, 0));
   CU(cudaMalloc(&h->d_rec, h->rec_bytes));
   CU(cudaMemset(h->d_rec, 0, h->rec_bytes));
-  CU(cudaMalloc(&h->d_actions, B * 8));
+  CU(cudaMalloc(&h->d_actions, B * 8 + 16));
   CU(cudaHostAlloc((void**)&h->h_actions, B * 8, cudaHostAllocMapped));
   memset(h->h_actions, 0, B * 8);
   CU(cudaHostGetDevicePointer((void**)&h->h_actions_dev, h->h_actions, 0));
@@ -276,6 +316,18 @@ static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int 
   h->rec_direct = 1;
   if (const char* e = getenv("L2S_HOST_ZEROCOPY")) h->zero_copy = atoi(e) != 0;
   if (const char* e = getenv("L2S_HOST_RECORDS")) h->rec_direct = atoi(e) != 0;
+  CU(cudaHostAlloc((void**)&h->h_flag, 64, cudaHostAllocMapped));
+  memset(h->h_flag, 0, 64);
+  CU(cudaHostGetDevicePointer((void**)&h->h_flag_dev, h->h_flag, 0));
+  h->flag_epoch = 0;
+  h->wait_flag = 0;
+  h->host_debug = 0;
+  h->rec_lines = 0;
+  h->act_prefetch = 0;
+  if (const char* e = getenv("L2S_HOST_DEBUG")) h->host_debug = atoi(e);
+  if (const char* e = getenv("L2S_HOST_LINES")) h->rec_lines = atoi(e) != 0;
+  if (const char* e = getenv("L2S_HOST_PREFETCH")) h->act_prefetch = atoi(e) != 0;
+  if (const char* e = getenv("L2S_HOST_WAIT")) h->wait_flag = (strcmp(e, "flag") == 0) && resolve_write32() != nullptr;
   return L2S_OK;
 }
 
@@ -305,7 +357,9 @@ int l2s_destroy(l2s_handle h) {
   cudaFree(h->st.durw); cudaFree(h->st.mch); cudaFree(h->st.walk); cudaFree(h->st.where);
   cudaFree(h->st.tabu); cudaFree(h->st.cur); cudaFree(h->st.inc); cudaFree(h->st.err);
   cudaFree((void*)h->st.pending_page);
+  cudaFree(h->st.fq); cudaFree(h->st.evalid);
   cudaFree(h->d_rec); cudaFreeHost(h->h_rec); cudaFree(h->d_actions); cudaFreeHost(h->h_actions);
+  cudaFreeHost(h->h_flag);
   free(h);
   return L2S_OK;
 }
@@ -385,6 +439,7 @@ static StepArgs step_args(l2s_handle h, const l2s_step_io* io) {
   a.st = h->st;
   a.B = h->B;
   a.pmax = h->pmax;
+  a.incremental = h->incremental;
   if (io) {
     a.actions = io->actions;
     a.high = io->high;
@@ -422,10 +477,23 @@ int l2s_step(l2s_handle h, const l2s_step_io* io, void* stream) {
   return r;
 }
 
+int l2s_set_option(l2s_handle h, const char* name, int value) {
+  if (!h || !name) return L2S_ERR_INVALID_ARG;
+  if (!strcmp(name, "host_wait_flag")) h->wait_flag = value != 0 && resolve_write32() != nullptr;
+  else if (!strcmp(name, "host_zero_copy")) h->zero_copy = value != 0;
+  else if (!strcmp(name, "host_records_direct")) h->rec_direct = value != 0;
+  else if (!strcmp(name, "host_record_lines")) h->rec_lines = value != 0;
+  else if (!strcmp(name, "host_action_prefetch")) h->act_prefetch = value != 0;
+  else if (!strcmp(name, "host_debug")) h->host_debug = value;
+  else if (!strcmp(name, "incremental")) h->incremental = value != 0 && h->st.fq != nullptr;
+  else return L2S_ERR_INVALID_ARG;
+  return L2S_OK;
+}
+
 int l2s_host_records(l2s_handle h, const uint32_t** records, int* stride_words, int32_t** actions) {
   if (!h) return L2S_ERR_INVALID_ARG;
   if (records) *records = h->h_rec;
-  if (stride_words) *stride_words = L2S_REC_HEADER_WORDS + h->pmax;
+  if (stride_words) *stride_words = h->rec_stride;
   if (actions) *actions = h->h_actions;
   return L2S_OK;
 }
@@ -456,7 +524,16 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
         cudaGetLastError();
     }
     if (!in_place || !h->zero_copy) memcpy(h->h_actions, actions_host, B * 8);   // pageable caller memory: stage it
-    if (h->zero_copy) {
+    const int32_t* src_dev = in_place ? in_place : h->h_actions_dev;
+    if (h->zero_copy && h->act_prefetch && !((uintptr_t)src_dev & 15u) && !((B * 8) & 15u)) {
+      // one small kernel pulls the whole action block over PCIe with 16-byte coalesced reads (512 requests of 128
+      // bytes instead of one 8-byte request per instance from the step kernel's warps)
+      const int n16 = (int)((B * 8 + 15) / 16);
+      copy16_kernel<<<(n16 + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4*>(in_place ? in_place : h->h_actions_dev),
+                                                      reinterpret_cast<uint4*>(h->d_actions), n16);
+      CU(cudaGetLastError());
+      a.actions = h->d_actions;
+    } else if (h->zero_copy) {
       a.actions = in_place ? in_place : h->h_actions_dev;
     } else {
       CU(cudaMemcpyAsync(h->d_actions, h->h_actions, B * 8, cudaMemcpyHostToDevice, s));
@@ -464,12 +541,33 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
     }
   }
   a.rec = h->rec_direct ? h->h_rec_dev : h->d_rec;
-  a.rec_stride = L2S_REC_HEADER_WORDS + h->pmax;
+  a.rec_stride = h->rec_stride;
+  a.rec_lines = h->rec_lines;
+  if (h->host_debug & 1) a.rec = h->d_rec;
+  if ((h->host_debug & 2) && a.actions) a.actions = h->d_actions;
   int r = launch_step(h, a, stream);
   if (r != L2S_OK) return r;
   if (!io->is_reset && a.actions) h->itr += 1;
   if (!h->rec_direct) CU(cudaMemcpyAsync(h->h_rec, h->d_rec, h->rec_bytes, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
+  if (h->wait_flag) {
+    const uint32_t epoch = ++h->flag_epoch;
+    if (resolve_write32()(s, (unsigned long long)(uintptr_t)h->h_flag_dev, epoch, 0u) != 0) return L2S_ERR_CUDA;
+    volatile uint32_t* flag = h->h_flag;
+    for (unsigned long long spins = 1; *flag != epoch; ++spins) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      if ((spins & 0xfffffull) == 0) {   // every ~million polls: a faulted launch would never write the flag
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q != cudaSuccess && q != cudaErrorNotReady) {
+          fprintf(stderr, "l2s_b200: CUDA error %s while waiting for a step\n", cudaGetErrorString(q));
+          return L2S_ERR_CUDA;
+        }
+      }
+    }
+  } else {
+    CU(cudaStreamSynchronize(s));
+  }
   if (pairs_host || npairs_host || status_host || reward_host || makespan_host || done_host) {
     const size_t stride = (size_t)a.rec_stride;
     for (size_t b = 0; b < B; ++b) {   // unpack the records; only the valid prefix of every pair row is defined

@@ -74,6 +74,10 @@ struct State {
   int32_t* inc;     // [B] incumbent makespan
   int32_t* err;     // [1] first device-side error: (code<<24)|instance  (0 = none)
   const int32_t* pending_page;   // [2*n1p] words of -1: source of the TMA fill of tq
+  // Incremental re-evaluation behind the step API (CTA-per-instance kernel only; nullptr otherwise): completion
+  // times and tails of the last evaluation, kept between launches, and a per-instance "matches walk" flag
+  int32_t* fq;      // [B][2*n1p]  fin | q exactly as they stand in shared memory after an evaluation
+  int32_t* evalid;  // [B]         1: fq[b] belongs to the current machine orders
 };
 
 // 32-bit shared-memory addressing (keeps the hot loops free of 64-bit generic pointer arithmetic)
@@ -174,8 +178,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // for small instances, the static node words; 16-byte aligned, sizes multiples of 16) that complete on an
 // mbarrier in the instance's scratch words; the "pending" sentinels of tq are bulk-copied from a page of -1 words
 // (L2 resident).  Every lane then waits on the barrier (phase 0; each instance slot is used once per kernel).
+// preload (CTA kernel): tq is bulk-copied from the cached evaluation st.fq instead of being filled with sentinels
 __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, const State& st, int b, int lane,
-                                               bool fill_q, int nthr = 32) {
+                                               bool fill_q, int nthr = 32, bool preload = false) {
   const uint32_t bar = s.misc + 8u, bar2 = s.misc + 16u;
   if (lane == 0) {
     const uint32_t wbytes = (uint32_t)L.walk_stride * 4u, dbytes = L.off_durw >= 0 ? (uint32_t)L.node_stride * 2u : 0u;
@@ -187,11 +192,13 @@ __device__ __forceinline__ void stage_instance(const Layout& L, const Inst& s, c
     mbar_init(bar2, 1);
     mbar_expect_tx(bar, wbytes);
     bulk_g2s(s.walk, st.walk + (size_t)b * L.walk_stride, wbytes, bar);
-    mbar_expect_tx(bar2, dbytes + tbytes);
+    const uint32_t pbytes = preload ? 2u * (uint32_t)L.n1p * 4u : 0u;
+    mbar_expect_tx(bar2, dbytes + tbytes + pbytes);
     if (tbytes) bulk_g2s(s.tq, st.pending_page, tbytes, bar2);
+    if (pbytes) bulk_g2s(s.tq, st.fq + (size_t)b * 2 * L.n1p, pbytes, bar2);
     if (dbytes) bulk_g2s(s.durw, st.durw + (size_t)b * L.node_stride, dbytes, bar2);
   }
-  if (nthr > 32) fill_pending(L, s, lane, fill_q, nthr);
+  if (nthr > 32 && !preload) fill_pending(L, s, lane, fill_q, nthr);
   if (nthr > 32) __syncthreads(); else __syncwarp();   // the barrier words are initialised before anyone polls them
   mbar_wait(bar, 0);
 }
@@ -223,9 +230,10 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
   const uint32_t a_nb = dir ? a_self + 4u : a_self - 4u;             // &tq[base +- 1]
   const unsigned bflag = dir ? kWLast : kWFirst;
   const int stepb = dir ? -4 : 4;                                    // walk step in bytes; also a_self - a_nb
-  // start / prev0 (forward only): resume the lane's row at position `start` with its machine predecessor's value
-  // prev0 (incremental re-evaluation: the operations before `start` keep their values)
-  uint32_t a_w = walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 : start));
+  // start / prev0: resume the lane's row behind its first `start` operations in sweep order (forward: from the head
+  // of the row, backward: from its end) with the value prev0 of the last operation that is kept (incremental
+  // re-evaluation: the operations before `start` keep their values)
+  uint32_t a_w = walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 - start : start));
   int left = active ? n_j - start : 0;                               // operations still to place
   int prevval = prev0;
   unsigned w = 0, wn = 0;
@@ -382,6 +390,46 @@ __device__ __forceinline__ int evaluate_forward_from(const Layout& L, const Inst
   const bool ok = wavefront(L, s, lane, 0, active, last, -1, 0u, start, prev0);
   const int ms = __reduce_max_sync(kFull, last);
   return ok ? ms : -1;
+}
+
+// ---- incremental re-evaluation behind the step API (CTA kernel) --------------------------------------------------
+// tq holds the completion times fin and tails q of the evaluation BEFORE the swap of the adjacent pair a0 -> a1 (now
+// a1 at walk position i0, a0 at i0+1).  Only descendants of the pair can change their earliest start, only ancestors
+// their tail:
+//   forward : every descendant has an old earliest start >= thr_f = old est(a0); operations below that threshold keep
+//             fin (the set is closed under predecessors) and form a PREFIX of every machine row (est grows along a row);
+//   backward: every ancestor has an old tail-after-completion q - dur >= thr_b = old q(a1) - dur(a1); operations below
+//             keep q and form a SUFFIX of every row.
+// resume_point: binary search of the lane's row (uniform trip count) for the number of kept operations in sweep order
+// and the value of the last kept one.  Must run BEFORE invalidate_from resets the others to "pending".
+__device__ __forceinline__ void resume_point(const Layout& L, const Inst& s, int m, int dir, bool active, int thr,
+                                             int& start, int& prev0) {
+  const int n_j = L.n_j;
+  const uint32_t val = s.tq + (dir ? 4u * L.n1p : 0u);
+  const uint32_t row = s.walk + 4u * (uint32_t)((active ? m : 0) * n_j);
+  int lo = 0, hi = active ? n_j : 0;
+  for (int span = n_j; span > 0; span >>= 1) {
+    if (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const unsigned w = (unsigned)lds32(row + 4u * (dir ? n_j - 1 - mid : mid));
+      const int head = lds32(val + 4u * (w & kWId)) - (int)(w >> kWDurShift);
+      if (head < thr) lo = mid + 1; else hi = mid;
+    }
+  }
+  start = lo;
+  prev0 = 0;
+  if (lo > 0) prev0 = lds32(val + 4u * ((unsigned)lds32(row + 4u * (dir ? n_j - lo : lo - 1)) & kWId));
+}
+// every value at or above its threshold goes back to "pending" (all threads of the CTA)
+__device__ __forceinline__ void invalidate_from(const Layout& L, const Inst& s, int thr_f, int thr_b, int tid, int nthr) {
+  const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
+  for (int i = tid; i < L.n; i += nthr) {
+    const unsigned w = (unsigned)lds32(s.walk + 4u * i);
+    const uint32_t o = 4u * (w & kWId);
+    const int d = (int)(w >> kWDurShift);
+    if (lds32(fin + o) - d >= thr_f) sts32(fin + o, -1);
+    if (lds32(q + o) - d >= thr_b) sts32(q + o, -1);
+  }
 }
 
 // Data-parallel pass over the walk words after an evaluation: for every operation record

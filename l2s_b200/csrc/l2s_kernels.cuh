@@ -54,6 +54,7 @@ __device__ __forceinline__ void reset_dynamic(const State& st, int b, int lane) 
     st.tabu[2 * b + 1] = 0;
     st.cur[b] = 0;
     st.inc[b] = 0;
+    if (st.evalid) st.evalid[b] = 0;   // a new solution: the cached evaluation is void
   }
 }
 
@@ -257,6 +258,12 @@ __global__ void build_initial_kernel(Layout L, InitLayout IL, State st, int B, i
   reset_dynamic(st, b, lane);
 }
 
+// 16-byte coalesced copy (host action block -> device staging, see l2s_step_host)
+__global__ void copy16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) dst[i] = src[i];
+}
+
 // ------------------------------------------------------------------------------------------------------
 // The environment step: JsspN5.step (env/environment.py:356-387), one launch for the whole slice.
 // ------------------------------------------------------------------------------------------------------
@@ -304,7 +311,9 @@ struct StepArgs {
   //   word 0: npairs | done << 16 | (status & 0xff) << 24;  words 1-3: makespan, reward, incumbent (float32);
   //   words 4..4+npairs: the feasible pairs, a0 | a1 << 16
   uint32_t* rec;
-  int rec_stride;          // words per record = 4 + pmax
+  int rec_stride;          // words per record: 4 + pmax rounded up to a multiple of 16
+  int rec_lines;           // write whole 64-byte lines (the words behind 4 + npairs are padding with stale contents)
+  int incremental;         // CTA kernel: resume the sweeps from the cached evaluation st.fq (0: always sweep everything)
   // test introspection (l2s_export_state): evaluate only, no mutation
   int export_only;
   int32_t* ex_est;
@@ -549,7 +558,8 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
   if (rec) {
     __syncwarp();
     uint32_t* r = rec + (size_t)b * a.rec_stride;
-    for (int i = lane; i < 4 + np; i += 32) r[i] = (uint32_t)lds32(stage + 4u * i);
+    const int nw_rec = a.rec_lines ? ((4 + np + 15) & ~15) : 4 + np;
+    for (int i = lane; i < nw_rec; i += 32) r[i] = (uint32_t)lds32(stage + 4u * i);
   }
   TL(10); TL(1);
 }
@@ -593,7 +603,10 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     for (int k = 0; k < kPairRegs; ++k)
       dpair[k] = __ldg(reinterpret_cast<const unsigned*>(gdurw) + min(tid + k * nthr, (n1 >> 1) - 1));
   }
-  stage_instance(L, s, a.st, b, tid, true, nthr);
+  // incremental re-evaluation: the completion times / tails of the previous evaluation come back from HBM
+  // (one more bulk copy on the second barrier) instead of "pending" sentinels
+  const bool cached = a.incremental && a.st.evalid && a.st.evalid[b] != 0;
+  stage_instance(L, s, a.st, b, tid, true, nthr, cached);
   __syncthreads();
   if (a0 >= 1 && a0 <= n) {
     for (int i = tid; i < n; i += nthr)
@@ -614,34 +627,57 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
       if (has_t) gw[i0 + 2] = (uint32_t)lds32(s.walk + 4u * (i0 + 2));
       a.st.tabu[2 * b] = a1;
       a.st.tabu[2 * b + 1] = a0;
+      if (a.st.evalid) a.st.evalid[b] = 0;   // until this launch has stored the new evaluation
     }
   }
   __syncthreads();
-  {
-    const int r = sh[1];
-    if (r == 0) { tabu0 = a1; tabu1 = a0; } else if (r < 0) status = r;
-  }
+  const int swap_r = sh[1];
+  if (swap_r == 0) { tabu0 = a1; tabu1 = a0; } else if (swap_r < 0) status = swap_r;
   TLC(4);
   stage_wait_rest(s);
   // evaluation: forward sweep on warp 0, backward sweep on warp 1 (or both on warp 0 if the CTA has one warp).
+  // With a cached evaluation nothing is swept when nothing moved, and after a swap only the part of the schedule
+  // that can change (see resume_point): the rows resume behind their kept prefix (forward) / suffix (backward).
+  int startv = 0, prevv = 0, start2 = 0, prev2 = 0;     // resume points of this lane's row (warp 0: fwd[, bwd]; warp 1: bwd)
+  const bool sweep = !cached || swap_r == 0;
+  if (cached && swap_r == 0) {
+    const unsigned wa1 = (unsigned)lds32(s.walk + 4u * i0), wa0 = (unsigned)lds32(s.walk + 4u * (i0 + 1));
+    const int thr_f = lds32(s.tq + 4u * (wa0 & kWId)) - (int)(wa0 >> kWDurShift);                 // old est(a0)
+    const int thr_b = lds32(s.tq + 4u * (L.n1p + (wa1 & kWId))) - (int)(wa1 >> kWDurShift);       // old tail after a1
+    if (w == 0) {
+      resume_point(L, s, lane, 0, lane < L.n_m, thr_f, startv, prevv);
+      if (nw == 1) resume_point(L, s, lane, 1, lane < L.n_m, thr_b, start2, prev2);
+    } else if (w == 1) {
+      resume_point(L, s, lane, 1, lane < L.n_m, thr_b, startv, prevv);
+    }
+    __syncthreads();                       // every resume point is read from the OLD values
+    invalidate_from(L, s, thr_f, thr_b, tid, nthr);
+    __syncthreads();
+  }
   // __syncthreads does not reconverge a warp whose lanes arrived separately (lane 0 took the write-back branch
   // above): without the explicit __syncwarp the sweep below would run with the warp split in two, every level
   // paying the divergent path of its own __syncwarp (measured: 255 ns instead of 64 ns per level)
   __syncwarp();
-  if (w == 0) {
-    int last;
-    const bool ok = wavefront(L, s, lane, 0, lane < L.n_m, last);
-    const int ms0 = __reduce_max_sync(kFull, last);
-    if (lane == 0) { sh[3] = ms0; sh[4] = ok; }
-    if (nw == 1) {
+  if (sweep) {
+    if (w == 0) {
+      int last;
+      const bool ok = wavefront(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv);
+      const int ms0 = __reduce_max_sync(kFull, last);
+      if (lane == 0) { sh[3] = ms0; sh[4] = ok; }
+      if (nw == 1) {
+        int l2;
+        const bool ok2 = wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2);
+        if (lane == 0) sh[5] = ok2;
+      }
+    } else if (w == 1) {
       int l2;
-      const bool ok2 = wavefront(L, s, lane, 1, lane < L.n_m, l2);
+      const bool ok2 = wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv);
       if (lane == 0) sh[5] = ok2;
     }
-  } else if (w == 1) {
-    int l2;
-    const bool ok2 = wavefront(L, s, lane, 1, lane < L.n_m, l2);
-    if (lane == 0) sh[5] = ok2;
+  } else if (tid == 0) {                   // nothing moved: the cached evaluation stands (fin[T] = makespan)
+    sh[3] = lds32(s.tq + 4u * (n + 1));
+    sh[4] = 1;
+    sh[5] = 1;
   }
   __syncthreads();
   TLC(5);
@@ -671,6 +707,13 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     sts32(q + 4u * (n + 1), 0);
   }
   __syncthreads();
+  if (a.incremental && a.st.fq && sweep && !a.export_only) {
+    // keep this evaluation for the next launch: 16-byte coalesced copies of fin | q, then the flag (the next launch
+    // on the stream sees both; a kernel that changes the machine orders clears the flag)
+    uint4* g = reinterpret_cast<uint4*>(a.st.fq + (size_t)b * 2 * L.n1p);
+    for (int i = tid; i < L.n1p / 2; i += nthr) g[i] = lds128(s.tq + 16u * i);
+    if (tid == 0) a.st.evalid[b] = 1;
+  }
   if (a.x) {
     float* xo = a.x + (size_t)b * n1 * 3;
     const float fms = (float)ms;
@@ -820,7 +863,8 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   if (rec) {
     __syncwarp();
     uint32_t* r = rec + (size_t)b * a.rec_stride;
-    for (int i = lane; i < 4 + np; i += 32) r[i] = (uint32_t)lds32(stage + 4u * i);
+    const int nw_rec = a.rec_lines ? ((4 + np + 15) & ~15) : 4 + np;
+    for (int i = lane; i < nw_rec; i += 32) r[i] = (uint32_t)lds32(stage + 4u * i);
   }
   TLC(10); TLC(1);
 }
@@ -1021,6 +1065,7 @@ __global__ void run_kernel(const __grid_constant__ RunArgs a) {
     a.st.tabu[2 * b + 1] = tabu1;
     a.st.cur[b] = cur;
     a.st.inc[b] = inc;
+    if (a.st.evalid) a.st.evalid[b] = 0;   // the machine orders moved on: the step kernel's cached evaluation is void
     if (status) record_error(a.st.err, status, b);
   }
 }

@@ -59,6 +59,15 @@ int l2s_parse_actions(PyObject* actions, int32_t* out, int B) {
   }
   for (int b = 0; b < B; ++b) {
     PyObject* item = PySequence_Fast_GET_ITEM(fast, b);
+    /* common case: an exact list of two exact ints -- no temporaries */
+    if (PyList_CheckExact(item) && PyList_GET_SIZE(item) == 2 && PyLong_CheckExact(PyList_GET_ITEM(item, 0)) &&
+        PyLong_CheckExact(PyList_GET_ITEM(item, 1))) {
+      const long v0 = PyLong_AsLong(PyList_GET_ITEM(item, 0)), v1 = PyLong_AsLong(PyList_GET_ITEM(item, 1));
+      if ((v0 == -1 || v1 == -1) && PyErr_Occurred()) { Py_DECREF(fast); return -1; }
+      out[2 * b] = (int32_t)v0;
+      out[2 * b + 1] = (int32_t)v1;
+      continue;
+    }
     PyObject* pf = PySequence_Fast(item, "every action must be a pair [a0, a1]");
     if (!pf) { Py_DECREF(fast); return -1; }
     if (PySequence_Fast_GET_SIZE(pf) != 2) {

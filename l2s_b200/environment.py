@@ -397,7 +397,7 @@ class JsspN5:
         B, device = self._key[0], self._device
         n1 = self.n_oprs + 2
         e_mc = self.n_mch * (self.n_job - 1)
-        pm = self._h_rec.shape[1] - _capi.REC_HEADER_WORDS
+        pm = self._lib.l2s_pmax(self._h)       # (the host records are padded to whole 64-byte lines: not their width)
         return dict(x=torch.empty((B * n1, 3), dtype=torch.float32, device=device),
                     emc=torch.empty((2, B * e_mc), dtype=torch.int64, device=device),
                     ms=torch.empty((B, 1), dtype=torch.float32, device=device),
@@ -505,7 +505,9 @@ class JsspN5:
             _raise_status(int(status[b]), b, "step")
         self.current_objs = ms
         self.incumbent_objs = inc
-        fa = MoveLists(rec.copy())       # the pinned records are overwritten by the next step: snapshot (~1 MB memcpy)
+        # the pinned records are overwritten by the next step: snapshot the header + the longest valid pair list
+        width = _capi.REC_HEADER_WORDS + max(1, int((head & 0xffff).max()))
+        fa = MoveLists(rec[:, :width].copy())
         self._fa = fa
         self._flag = ~done
         return (x, self._const[0], emc, self._const[1]), reward, fa, done

@@ -255,3 +255,74 @@ def test_evaluator_workspace_is_handed_back_clean():
         assert torch.equal(est.reshape(B, n1), ex["est"].float()) and torch.equal(lst.reshape(B, n1), ex["lst"].float())
         assert torch.equal(ms, env.current_objs)
         assert int(ev._ws.count_nonzero()) == 0
+
+
+@pytest.mark.parametrize("n_j,n_m,B,K,cta", [(100, 20, 24, 40, None), (150, 25, 8, 25, None), (30, 20, 40, 60, "4"),
+                                              (20, 15, 50, 60, "2"), (12, 7, 30, 80, "1")])
+def test_incremental_step_equals_full_sweep_and_c_oracle(n_j, n_m, B, K, cta, monkeypatch):
+    """The CTA step kernel resumes its forward / backward sweeps from the evaluation it kept in HBM.  The same long
+    trajectory (random feasible moves with dummy moves, evaluate-only launches, a fused run and an illegal action in
+    between) must give bit-identical outputs at every step as a handle created with L2S_INCREMENTAL=0 (always sweeps
+    everything) and as the plain-C oracle."""
+    from l2s_b200 import JsspN5
+    from oracle import c_oracle as CO
+    import networkx as nx
+    if cta:
+        monkeypatch.setenv("L2S_CTA_WARPS", cta)           # force the CTA kernel for shapes that default to the warp kernel
+    inst = gen_instances(n_j, n_m, B, seed=31 + n_j)
+    monkeypatch.setenv("L2S_INCREMENTAL", "1")
+    inc = JsspN5(n_j, n_m, 1, 99)
+    s_i, fa_i, _ = inc.reset(inst, "fdd-divide-mwkr", "cuda")
+    monkeypatch.setenv("L2S_INCREMENTAL", "0")
+    full = JsspN5(n_j, n_m, 1, 99)
+    s_f, fa_f, _ = full.reset(inst, "fdd-divide-mwkr", "cuda")
+    monkeypatch.delenv("L2S_INCREMENTAL")
+    cenv = CO.CEnv(inst, inc.solutions().cpu().numpy())
+    rng = np.random.RandomState(3)
+
+    def same(tag):
+        assert torch.equal(s_i[0], s_f[0]) and torch.equal(s_i[2], s_f[2]), tag
+        assert fa_i == fa_f, tag
+        assert torch.equal(inc.current_objs, full.current_objs) and torch.equal(inc.incumbent_objs, full.incumbent_objs), tag
+
+    same("reset")
+    for k in range(K):
+        acts = []
+        for f in fa_i:
+            p = f[rng.randint(len(f))]
+            acts.append([0, 0] if rng.rand() < 0.1 else [int(p[0]), int(p[1])])     # 10 % dummy moves
+        s_i, r_i, fa_i, d_i = inc.step(acts, "cuda")
+        s_f, r_f, fa_f, d_f = full.step(acts, "cuda")
+        cenv.run("replay", 1, tape=np.array(acts, dtype=np.int32).reshape(B, 1, 2), write_state=True)
+        same("step %d" % k)
+        assert torch.equal(r_i, r_f) and torch.equal(d_i, d_f)
+        assert np.array_equal(s_i[0].cpu().numpy(), cenv.x) and np.array_equal(s_i[2].cpu().numpy(), cenv.emc), k
+        if k % 9 == 4:          # evaluate-only launches use the cached evaluation unchanged
+            s_i, fa_i, _ = inc.observe()
+            s_f, fa_f, _ = full.observe()
+            same("observe %d" % k)
+            ex_i, ex_f = inc.export_state(), full.export_state()
+            assert torch.equal(ex_i["est"], ex_f["est"]) and torch.equal(ex_i["lst"], ex_f["lst"])
+            assert np.array_equal(ex_i["est"].cpu().numpy(), cenv.est) and np.array_equal(ex_i["lst"].cpu().numpy(), cenv.lst)
+        if k == K // 2:         # a fused run moves the machine orders without the step kernel: the cache must be dropped
+            inc.run("random", 7, seed=5)
+            full.run("random", 7, seed=5)
+            cenv.run("random", 7, seed=5)
+            s_i, fa_i, _ = inc.observe()
+            s_f, fa_f, _ = full.observe()
+            same("after run")
+        if k == K // 3:         # an illegal action is reported and leaves state and cache untouched
+            bad = [list(map(int, f[0])) for f in fa_i]
+            bad[0] = [1, 1 + n_m]           # first operations of jobs 0 and 1: never an adjacent machine pair? (only if same machine)
+            if inst[0, 1, 0, 0] != inst[0, 1, 1, 0]:
+                with pytest.raises(nx.NetworkXError):
+                    inc.step(bad, "cuda")
+                with pytest.raises(nx.NetworkXError):
+                    full.step(bad, "cuda")
+                cenv.run("replay", 1, tape=np.array([[0, 0]] + bad[1:], dtype=np.int32).reshape(B, 1, 2), write_state=True)
+                inc.itr += 1
+                full.itr += 1
+                s_i, fa_i, _ = inc.observe()
+                s_f, fa_f, _ = full.observe()
+                same("after illegal action")
+                assert np.array_equal(s_i[0].cpu().numpy(), cenv.x)
