@@ -5,7 +5,9 @@ import os, subprocess, sys, ctypes as C
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TL_LIB = os.path.join(ROOT, "l2s_b200", "lib", "libl2s_b200_timeline.so")
-if not os.path.isfile(TL_LIB):
+_src = os.path.join(ROOT, "l2s_b200", "csrc")
+if not os.path.isfile(TL_LIB) or any(os.path.getmtime(os.path.join(_src, f)) > os.path.getmtime(TL_LIB)
+                                     for f in ("l2s_capi.cu", "l2s_kernels.cuh", "l2s_device.cuh")):
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
                     "-Xcompiler", "-fPIC", "-DL2S_TIMELINE", "-o", TL_LIB, "l2s_capi.cu"],
                    cwd=os.path.join(ROOT, "l2s_b200", "csrc"), check=True)
