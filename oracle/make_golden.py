@@ -162,13 +162,54 @@ def greedy(R, ds, log_steps, seed=1):
                         stored_rows=stored, stored_steps=np.array([500, 1000, 2000, 5000]))
 
 
+def plist(R, name="plist_10x5", n_j=10, n_m=5, B=6, K=40, seed=7):
+    """`init_type='plist'` (JsspN5._p_list_solver, env/environment.py:140-200, :391-393): one random priority list
+    (drawn from np.random at reset) shared by the batch.  Stores the reference's initial machine orders, first state
+    and a K-step trajectory."""
+    np.random.seed(21)
+    instances = np.array([R.uni_instance_gen(n_j, n_m, 1, 99) for _ in range(B)]).astype(np.int32)
+    np.random.seed(seed)
+    env = R.JsspN5(n_j, n_m, 1, 99)
+    state, fa, done = env.reset(instances, "plist", "cpu")
+    n1 = n_j * n_m + 2
+    emc = state[2].numpy()
+    E = emc.shape[1] // B
+    mseq0 = np.stack([mseq_from_emc(emc[:, b * E:(b + 1) * E] - b * n1, instances[b, 1], n_j, n_m) for b in range(B)])
+    oenv = O.OracleEnv(n_j, n_m, 1, 99)
+    ostate, ofa, odone = oenv.reset(instances, mseq=mseq0)
+    assert np.array_equal(state[0].numpy(), ostate[0]) and np.array_equal(emc, ostate[2])
+    x_first, ms_first = state[0].numpy().copy(), env.current_objs.numpy().reshape(-1).copy()
+    p0, c0 = pad_pairs(fa, 32)
+    rnd = random.Random(seed)
+    tape, ms, pairs, npairs = [], [], [], []
+    for k in range(K):
+        acts = [list(map(int, rnd.choice(f))) for f in fa]
+        state, r, fa, done = env.step(acts, "cpu")
+        ostate, orr, ofa, odone = oenv.step(acts)
+        assert np.array_equal(state[0].numpy(), ostate[0]) and np.array_equal(r.numpy(), orr)
+        tape.append(np.array(acts, dtype=np.int32))
+        ms.append(env.current_objs.numpy().reshape(-1).astype(np.int32))
+        p, c = pad_pairs(fa, 32)
+        pairs.append(p)
+        npairs.append(c)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), instances=instances, mseq0=mseq0.astype(np.int32),
+                        seed=np.array(seed), x_first=x_first, emc_first=emc, makespan_first=ms_first, pairs_first=p0,
+                        npairs_first=c0, tape=np.stack(tape, axis=1), makespan=np.stack(ms), pairs=np.stack(pairs),
+                        npairs=np.stack(npairs), x_last=state[0].numpy(), meta=np.array([n_j, n_m, 99, 1000]))
+    print("plist", name, "makespans", ms_first)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--greedy", action="store_true", help="also run the (slow) reference greedy baseline")
     ap.add_argument("--only-greedy", action="store_true")
+    ap.add_argument("--only-plist", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     R = ref_harness.load()
+    if args.only_plist:
+        plist(R)
+        return
     if not args.only_greedy:
         trajectory(R, "6x6_ties", 6, 6, 8, 120, 1, 4, 1)
         trajectory(R, "10x10_ties", 10, 10, 6, 100, 1, 3, 2)
@@ -181,6 +222,7 @@ def main():
         trajectory(R, "30x20", 30, 20, 2, 30, 1, 99, 10)
         trajectory(R, "50x20", 50, 20, 1, 12, 1, 99, 12)
         evaluator_coo(R)
+        plist(R)
     if args.greedy or args.only_greedy:
         greedy(R, "ft6x6", [10, 50, 100, 500])
         greedy(R, "la10x5", [10, 50, 100, 500])

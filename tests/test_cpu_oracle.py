@@ -255,3 +255,15 @@ def test_python_list_glue_matches_numpy_route():
         g.l2s_parse_actions([[1, 2, 3]] * B, out.ctypes.data, B)
     with pytest.raises(TypeError):
         g.l2s_parse_actions([[1.5, 2]] * B, out.ctypes.data, B)
+
+
+def test_plist_initial_orders_match_reference_golden():
+    """a-14: `init_type='plist'` (env/environment.py:140-200, 391-393): with the numpy RNG seeded like the reference
+    run that produced tests/golden/plist_10x5.npz, the drop-in's host-side order construction yields the reference's
+    machine orders (the one RNG draw is the same `np.random.permutation` call)."""
+    from l2s_b200 import JsspN5
+    g = np.load(os.path.join(GOLDEN, "plist_10x5.npz"))
+    n_j, n_m = int(g["meta"][0]), int(g["meta"][1])
+    np.random.seed(int(g["seed"]))
+    got = JsspN5(n_j, n_m, 1, 99)._plist_orders(g["instances"])
+    assert np.array_equal(got, g["mseq0"])

@@ -318,3 +318,25 @@ def test_step_host_reads_pinned_caller_memory_in_place():
         recs.append(out)
     for (r0, x0), (r1, x1) in zip(*recs):
         assert np.array_equal(r0, r1) and np.array_equal(x0, x1)
+
+
+def test_plist_reset_matches_reference_golden():
+    """a-14: reset(init_type='plist') under the reference run's numpy seed reproduces its first state, move sets and a
+    40-step trajectory (tests/golden/plist_10x5.npz, generated from the unmodified reference)."""
+    from l2s_b200 import JsspN5
+    g = np.load(os.path.join(GOLDEN, "plist_10x5.npz"))
+    n_j, n_m = int(g["meta"][0]), int(g["meta"][1])
+    env = JsspN5(n_j, n_m, 1, 99)
+    np.random.seed(int(g["seed"]))
+    state, fa, done = env.reset(g["instances"], "plist", "cuda")
+    assert np.array_equal(env.solutions().cpu().numpy(), g["mseq0"])
+    assert np.array_equal(state[0].cpu().numpy(), g["x_first"]) and np.array_equal(state[2].cpu().numpy(), g["emc_first"])
+    assert np.array_equal(env.current_objs.cpu().numpy().reshape(-1), g["makespan_first"])
+    p, c = _pairs_from_fa(fa, 32)
+    assert np.array_equal(p, g["pairs_first"]) and np.array_equal(c, g["npairs_first"])
+    for k in range(g["tape"].shape[1]):
+        state, reward, fa, done = env.step(g["tape"][:, k].tolist(), "cuda")
+        assert np.array_equal(env.current_objs.cpu().numpy().reshape(-1).astype(np.int32), g["makespan"][k])
+        p, c = _pairs_from_fa(fa, 32)
+        assert np.array_equal(p, g["pairs"][k]) and np.array_equal(c, g["npairs"][k])
+    assert np.array_equal(state[0].cpu().numpy(), g["x_last"])
