@@ -55,10 +55,18 @@ Layout make_layout(int n_j, int n_m, bool stage_durw = false, int pmax = 0) {
   }
   // host record staging (4 + pmax words): the critical-predecessor array is dead by then; tiny instances get
   // their own region
+  // ... and so do the n5_moves scratch bits (one per path position), behind the record staging
+  const int rec_bytes = ru(4 + pmax, 16) * 4, bits_bytes = ru(4 * (L.n / 32 + 2), 16);
   L.off_rec = L.off_crit;
-  if (ru(4 + pmax, 16) * 4 > L.node_stride * 2) {
+  L.off_bits = L.off_crit + rec_bytes;
+  if (rec_bytes + bits_bytes > L.node_stride * 2) {
     L.off_rec = off;
-    off += ru(4 + pmax, 16) * 4;
+    off += rec_bytes;
+    L.off_bits = L.off_crit;
+    if (bits_bytes > L.node_stride * 2) {   // (only degenerate shapes)
+      L.off_bits = off;
+      off += bits_bytes;
+    }
   }
   L.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   L.bytes = ru(off, 16);
@@ -115,6 +123,7 @@ struct l2s_handle_s {
   long long itr;
   int warps_step, warps_run, warps_init;
   int cta_warps;   // > 0: large instances -> step_kernel_cta with this many warps per instance
+  int fast_sweep;  // CTA kernel: latency variant of the sweep (at most 4 instances resident per SM)
   int incremental; // CTA kernel: keep fin / q of the last evaluation in HBM and resume the sweeps from them
   size_t run_stride, run_stride_greedy;
   int run_off_where, run_off_plist, run_off_walk2;
@@ -255,6 +264,10 @@ static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int 
       if (v > 0) { h->cta_warps = v; }
     }
     if (h->cta_warps > 8) h->cta_warps = 8;
+    // few resident instances: the sweep warps are alone on their schedulers and a level costs its dependent chain ->
+    // latency variant; many: the schedulers are saturated by sweep instructions -> lean variant (l2s_device.cuh)
+    h->fast_sweep = h->cta_warps > 0 && resident <= 4;
+    if (const char* e = getenv("L2S_FAST_SWEEP")) h->fast_sweep = atoi(e) != 0;
   }
   CU(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax - 1024));   // it also has static shared memory
   CU(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -277,13 +290,17 @@ static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int 
   CU(cudaMalloc(&st.err, 4));
   // incremental re-evaluation behind the step API: only the CTA kernel (large instances, where sweep levels are a
   // third to a half of a step) keeps the last evaluation; L2S_INCREMENTAL=0 turns it off (experiments, tests)
-  h->incremental = h->cta_warps > 0;
-  if (const char* e = getenv("L2S_INCREMENTAL")) h->incremental = h->incremental && atoi(e) != 0;
-  if (h->incremental) {
+  // Measured: the sweep depth of a resumed evaluation halves, but the forward and the backward sweep
+  // run side by side, so the wall-clock depth is max(u, 1-u) ~ 0.75 of a full one and the saving (0.6 us of 7.8 at
+  // 100x20) is eaten by the extra state traffic and passes: OFF by default, l2s_set_option("incremental", 1) or
+  // L2S_INCREMENTAL=1 turns it on.
+  if (h->cta_warps > 0) {
     CU(cudaMalloc(&st.fq, B * 2 * (size_t)L.n1p * 4));
     CU(cudaMalloc(&st.evalid, B * 4));
     CU(cudaMemset(st.evalid, 0, B * 4));
   }
+  h->incremental = 0;
+  if (const char* e = getenv("L2S_INCREMENTAL")) h->incremental = st.fq != nullptr && atoi(e) != 0;
   {
     int32_t* page = nullptr;
     CU(cudaMalloc(&page, (size_t)2 * L.n1p * 4));
@@ -427,7 +444,9 @@ static int launch_step(l2s_handle h, const StepArgs& a, void* stream) {
     return L2S_OK;
   }
   const int W = h->warps_step;
-  step_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * h->L.bytes, (cudaStream_t)stream>>>(a);
+  static int pad = -1;   // experiments: extra dynamic shared memory per CTA (bytes) to cap the CTAs resident per SM
+  if (pad < 0) { const char* e = getenv("L2S_STEP_SMEM_PAD"); pad = e ? atoi(e) : 0; }
+  step_kernel<<<(h->B + W - 1) / W, W * 32, (size_t)W * h->L.bytes + (size_t)pad, (cudaStream_t)stream>>>(a);
   CU(cudaGetLastError());
   return L2S_OK;
 }
@@ -440,6 +459,7 @@ static StepArgs step_args(l2s_handle h, const l2s_step_io* io) {
   a.B = h->B;
   a.pmax = h->pmax;
   a.incremental = h->incremental;
+  a.fast_sweep = h->fast_sweep;
   if (io) {
     a.actions = io->actions;
     a.high = io->high;
@@ -486,6 +506,7 @@ int l2s_set_option(l2s_handle h, const char* name, int value) {
   else if (!strcmp(name, "host_action_prefetch")) h->act_prefetch = value != 0;
   else if (!strcmp(name, "host_debug")) h->host_debug = value;
   else if (!strcmp(name, "incremental")) h->incremental = value != 0 && h->st.fq != nullptr;
+  else if (!strcmp(name, "fast_sweep")) h->fast_sweep = value != 0;
   else return L2S_ERR_INVALID_ARG;
   return L2S_OK;
 }

@@ -59,6 +59,7 @@ struct Layout {
   int off_tq, off_walk, off_crit, off_misc;
   int off_durw;          // >= 0: static node words staged in shared memory (small instances); -1: read from HBM
   int off_rec;           // staging of the host record (4 + pmax words): overlays crit when that is large enough
+  int off_bits;          // n5_moves scratch (one bit per path position): in crit, behind the record staging if that overlays it
   unsigned magic_nm;     // floor(2^32 / n_m) + 1: (x mod n_m) by multiply-shift for x < 2^16
   int bytes;             // per instance (step kernel)
 };
@@ -121,6 +122,7 @@ struct Inst {            // shared-memory view of one instance (32-bit shared ad
   uint32_t durw;         // uint16 [node_stride] node words, valid iff Layout::off_durw >= 0
   uint32_t misc;         // int32 [4] parked scalars
   uint32_t rec;          // uint32 [4 + pmax] host record staging (valid after the critical path has been traced)
+  uint32_t bits;         // uint32 [n/32 + 2] n5_moves scratch (valid after the critical path has been traced)
 };
 
 __device__ __forceinline__ Inst inst_view(const Layout& L, uint32_t base) {
@@ -131,6 +133,7 @@ __device__ __forceinline__ Inst inst_view(const Layout& L, uint32_t base) {
   s.durw = base + (L.off_durw >= 0 ? L.off_durw : 0);
   s.misc = base + L.off_misc;
   s.rec = base + L.off_rec;
+  s.bits = base + L.off_bits;
   return s;
 }
 
@@ -216,6 +219,9 @@ __device__ __forceinline__ void stage_wait_rest(const Inst& s) { mbar_wait(s.mis
 // ------------------------------------------------------------------------------------------------------
 #ifdef L2S_TIMELINE
 __device__ unsigned long long g_dbg_levels[2] = {0ull, 0ull};   // diagnostic build: sum of level trips, number of sweeps
+#endif
+#ifndef L2S_LEVELS_PER_TRIP
+#define L2S_LEVELS_PER_TRIP 4
 #endif
 // half / walk: which half of tq the lane's values live in and which copy of the walk words it reads (defaults:
 // half = dir, the instance's own walk words); the greedy policy evaluates two neighbours at once with both
@@ -310,21 +316,122 @@ __device__ __forceinline__ bool wavefront(const Layout& L, const Inst& s, int m,
           : "r"(a_nb), "r"(bflag), "r"(stepb)
           : "memory");
     }
+  };
+  // L2S_LEVELS_PER_TRIP levels between two votes.  The level is straight-line predicated code, so a warp that enters
+  // converged stays converged and executes the levels in lock step (shared-memory stores of one level are visible to
+  // the loads of the next: same warp, program order); the warp is re-converged explicitly once per trip.
+  budget = (L.n + 2 * L2S_LEVELS_PER_TRIP - 1) / L2S_LEVELS_PER_TRIP;
+#ifdef L2S_TIMELINE
+  const int budget0 = budget;
+#endif
+  while (true) {
     __syncwarp();
+#pragma unroll
+    for (int k = 0; k < L2S_LEVELS_PER_TRIP; ++k) level();
+    if (!__any_sync(kFull, left > 0)) break;
+    if (--budget < 0) { last = prevval; return false; }
+  }
+#ifdef L2S_TIMELINE
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&g_dbg_levels[0], (unsigned long long)L2S_LEVELS_PER_TRIP * (unsigned long long)(budget0 - budget + 1)); atomicAdd(&g_dbg_levels[1], 1ull); }
+#endif
+  last = prevval;
+  return true;
+}
+
+// LATENCY variant of the wavefront (same arguments, same results).  When an SM holds only a few large instances
+// (batch of the order of the SM count), the sweep warps are alone on their schedulers and a level costs its dependent
+// chain, not its instruction count (measured at 100x20, 128 instances: 58 -> 41 ns per level, evaluation 7.8 -> 5.6 us).
+// With many resident instances the schedulers are saturated by sweep instructions instead and the leaner level of
+// `wavefront` (21 instead of 23 instructions) wins (100x20, 1024 instances: 37.4 vs 39.2 us), so the CTA kernel picks
+// per launch (StepArgs::fast_sweep).  Here the level keeps its dependent chain minimal:
+//   load neighbour value -> compare / add / max -> store own value, advance.
+// Everything else is decoded ONE OPERATION AHEAD, off the chain, from the prefetched next walk word: the address of
+// the value to wait for (A), of the own slot (As) and the duration (D).  Two reserved slots per direction replace the
+// flag tests: a job-first (forward) / job-last (backward) operation waits on the ZERO slot (S resp. T, value 0 while
+// the sweep runs) and a lane that has placed its whole row waits on the DEAD slot (T resp. S, value -1 = pending for
+// ever), so "ready" is always just nb >= 0.  The slots are written on entry (and S/T get their real values after the
+// sweeps, as before).
+__device__ __forceinline__ bool wavefront_fast(const Layout& L, const Inst& s, int m, int dir, bool active, int& last,
+                                          int half = -1, uint32_t walk = 0u, int start = 0, int prev0 = 0) {
+  const int n_j = L.n_j;
+  if (half < 0) half = dir;
+  if (walk == 0u) walk = s.walk;
+  const uint32_t base = s.tq + (half ? 4u * L.n1p : 0u);               // &val[0] of the lane's half
+  const uint32_t zero_a = base + (dir ? 4u * (uint32_t)(L.n + 1) : 0u);
+  const uint32_t dead_a = base + (dir ? 0u : 4u * (uint32_t)(L.n + 1));
+  const int nboff = dir ? 4 : -4;                                      // job neighbour: v+1 backward, v-1 forward
+  const unsigned bflag = dir ? kWLast : kWFirst;
+  const int stepb = dir ? -4 : 4;                                      // walk step in bytes
+  if (m == 0) { sts32(zero_a, 0); sts32(dead_a, -1); }
+  // start / prev0: resume the lane's row behind its first `start` operations in sweep order (forward: from the head
+  // of the row, backward: from its end) with the value prev0 of the last operation that is kept (incremental
+  // re-evaluation: the operations before `start` keep their values)
+  uint32_t a_w = walk + 4u * (uint32_t)(m * n_j + (dir ? n_j - 1 - start : start));
+  int left = active ? n_j - start : 0;                                 // operations still to place
+  unsigned w = 0, wn = 0;
+  if (left > 0) w = (unsigned)lds32(a_w);
+  if (left > 1) wn = (unsigned)lds32(a_w + stepb);
+  a_w += 2 * stepb;                                                    // the word that follows wn
+  uint32_t As = base + 4u * (w & kWId);
+  uint32_t A = (w & bflag) ? zero_a : As + nboff;
+  int D = (int)(w >> kWDurShift);
+  if (left <= 0) { A = dead_a; D = 0; }
+  int prevD = prev0 + D;                                               // value of the current operation if its machine predecessor decides
+  __syncwarp();
+  int budget = (L.n + 2 * L2S_LEVELS_PER_TRIP - 1) / L2S_LEVELS_PER_TRIP;   // a DAG needs at most n levels
+  // One level: place the lane's current operation if the value it waits for is final.  Straight-line predicated code
+  // (23 instructions): a warp that enters converged stays converged, so the shared-memory stores of one level are
+  // visible to the loads of the next (same warp, program order).  Equivalent C:
+  //   nb = *A;  [decode wn -> An, Asn, Dn; An = dead, Dn = 0 if wn is not an operation of this row]
+  //   if (nb >= 0) { val = max(prevD, nb + D); *As = val; prevD = val + Dn; A = An; As = Asn; D = Dn; --left;
+  //                  if (operations remain behind wn) wn = *a_w; a_w += stepb; }
+  auto level = [&]() {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pv, pf, pl, pq;\n\t"
+        ".reg .b32 nb, t, val, idn, asn, an, dn, tf;\n\t"
+        "ld.shared.b32 nb, [%0];\n\t"
+        "and.b32 idn, %5, 0xffff;\n\t"
+        "mad.lo.u32 asn, idn, 4, %7;\n\t"
+        "and.b32 tf, %5, %11;\n\t"
+        "setp.ne.u32 pf, tf, 0;\n\t"
+        "add.s32 an, asn, %10;\n\t"
+        "selp.b32 an, %8, an, pf;\n\t"
+        "setp.le.s32 pl, %4, 1;\n\t"
+        "selp.b32 an, %9, an, pl;\n\t"
+        "shr.u32 dn, %5, 20;\n\t"
+        "selp.b32 dn, 0, dn, pl;\n\t"
+        "setp.ge.s32 pv, nb, 0;\n\t"
+        "add.s32 t, nb, %2;\n\t"
+        "max.s32 val, %3, t;\n\t"
+        "@pv st.shared.b32 [%1], val;\n\t"
+        "setp.gt.and.s32 pq, %4, 2, pv;\n\t"
+        "@pv add.s32 %3, val, dn;\n\t"
+        "@pv mov.b32 %0, an;\n\t"
+        "@pv mov.b32 %1, asn;\n\t"
+        "@pv mov.b32 %2, dn;\n\t"
+        "@pv add.s32 %4, %4, -1;\n\t"
+        "@pq ld.shared.b32 %5, [%6];\n\t"
+        "@pv add.s32 %6, %6, %12;\n\t"
+        "}\n"
+        : "+r"(A), "+r"(As), "+r"(D), "+r"(prevD), "+r"(left), "+r"(wn), "+r"(a_w)
+        : "r"(base), "r"(zero_a), "r"(dead_a), "r"(nboff), "r"(bflag), "r"(stepb)
+        : "memory");
   };
 #ifdef L2S_TIMELINE
   const int budget0 = budget;
 #endif
   while (true) {
-    level();
-    level();
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < L2S_LEVELS_PER_TRIP; ++k) level();
     if (!__any_sync(kFull, left > 0)) break;
-    if (--budget < 0) { last = prevval; return false; }
+    if (--budget < 0) { last = prevD; return false; }
   }
 #ifdef L2S_TIMELINE
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&g_dbg_levels[0], 2ull * (unsigned long long)(budget0 - budget + 1)); atomicAdd(&g_dbg_levels[1], 1ull); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&g_dbg_levels[0], (unsigned long long)L2S_LEVELS_PER_TRIP * (unsigned long long)(budget0 - budget + 1)); atomicAdd(&g_dbg_levels[1], 1ull); }
 #endif
-  last = prevval;
+  last = prevD;     // a finished lane carries the value of its last operation (Dn = 0 behind the row)
   return true;
 }
 
@@ -512,43 +619,99 @@ __device__ __forceinline__ int trace_path(const Layout& L, const Inst& s, int ms
   return len;
 }
 
+// The same critical path for the CTA kernel, where the chase from T is the longest serial chain of a large instance
+// (113 / 161 hops at 100x20 / 150x25): all threads first square the critical-predecessor map twice (jump2 = crit o crit,
+// jump4 = jump2 o jump2; crit[S] = crit[T] = 0, so S is a fixed point), then ONE warp follows jump4 -- a quarter of the
+// dependent loads -- dropping an anchor every fourth path position, and fills the three operations behind every anchor
+// in parallel (crit[a], jump2[a], crit[jump2[a]]).
+__device__ __forceinline__ int path_start(const Layout& L, const Inst& s, int ms, int lane) {
+  // T lists the job-last operations by ascending job: the first one that attains the makespan wins
+  for (int j0 = 0; j0 < L.n_j; j0 += 32) {
+    const int j = j0 + lane;
+    const unsigned hit = __ballot_sync(kFull, j < L.n_j && lds32(s.tq + 4u * (j * L.n_m + L.n_m)) == ms);
+    if (hit) return (j0 + __ffs(hit) - 1) * L.n_m + L.n_m;
+  }
+  return 0;
+}
+__device__ __forceinline__ void square_map(uint32_t dst, uint32_t src, int n1, int tid, int nthr) {
+  for (int v = tid; v < n1; v += nthr) sts16(dst + 2u * v, lds16(src + 2u * lds16(src + 2u * v)));
+}
+__device__ __forceinline__ int trace_path_jump(const Layout& L, const Inst& s, int start, int lane, uint32_t rp,
+                                               uint32_t jump2, uint32_t jump4) {
+  int v = start, na = 0;
+  const int cap = (L.n + 3) / 4 + 1;
+  while (v != 0 && na < cap) {     // uniform across the warp (broadcast loads)
+    if (lane == 0) sts16(rp + 8u * na, v);
+    ++na;
+    v = lds16(jump4 + 2u * v);
+  }
+  __syncwarp();
+  int len = 0;
+  for (int a0 = 0; a0 < na; a0 += 32) {
+    const int a = a0 + lane;
+    if (a < na) {
+      const int A = lds16(rp + 8u * a);
+      const int c1 = lds16(s.crit + 2u * A), c2 = lds16(jump2 + 2u * A);
+      const int c3 = lds16(s.crit + 2u * c2);
+      if (c1) sts16(rp + 8u * a + 2u, c1);
+      if (c2) sts16(rp + 8u * a + 4u, c2);
+      if (c3) sts16(rp + 8u * a + 6u, c3);
+      if (a == na - 1) len = 4 * a + 1 + (c1 != 0) + (c2 != 0) + (c3 != 0);
+    }
+  }
+  len = __reduce_max_sync(kFull, len);
+  __syncwarp();
+  return len;
+}
+
 // N5 block-boundary pairs in path order with the tabu filter: JsspN5._get_pairs (env/environment.py:84-105).
-// Two consecutive path operations are on the same machine iff the hop between them is not a job arc.
-// emit(idx, a0, a1) is called by the owning lane for pair number idx; returns the pair count, or a negative
-// status (-9: the reference's IndexError corner).
+// Two consecutive path operations are on the same machine iff the hop between them is not a job arc.  With
+// s_i = "path operations i and i+1 share a machine" (0 <= i < rg = len-1) and the sentinels s_(-1) = s_rg = 1 the
+// reference's case analysis collapses to   take_i = s_i and not (s_(i-1) and s_(i+1))   (first pair of every block
+// except a >= 3-long first block, last pair of every block except the last block, each pair once).  Pass 1 writes the
+// s bits as ballot words to the scratch `bits` (in the dead critical-predecessor array), pass 2 is branch-free bit
+// logic plus the tabu filter.  emit(idx, a0, a1) is called by the owning lane for pair number idx; returns the pair
+// count, or a negative status (-9: the reference's IndexError corner, a two-operation path on one machine).
 template <typename Emit>
 __device__ __forceinline__ int n5_moves(const Layout& L, const Inst& s, uint32_t rp, int len, int tabu0, int tabu1,
                                         int lane, Emit emit) {
   const int rg = len - 1;
+  if (rg <= 0) return 0;
+  const uint32_t bits = s.bits;
+  const uint32_t last = rp + 2u * (uint32_t)(len - 1);          // path position i lives at last - 2*i (rp is reversed)
+  const int kmax = rg >> 5;                                      // the word that holds the sentinel bit rg
+  for (int k = 0; k <= kmax; ++k) {
+    const int i = 32 * k + lane;
+    bool same = i == rg;
+    if (i < rg) {
+      const int u = lds16(last - 2u * i), w = lds16(last - 2u * i - 2u);
+      same = !(u == w - 1 && !is_job_first(L, w));
+    }
+    const unsigned bal = __ballot_sync(kFull, same);
+    if (lane == 0) sts32(bits + 4u * k, (int)bal);
+  }
+  __syncwarp();
+  const unsigned below = (1u << lane) - 1u;
   int count = 0;
-  int err = 0;
-  auto pf = [&](int i) -> int { return lds16(rp + 2u * (len - 1 - i)); };
-  auto same = [&](int i) -> bool {   // ops i and i+1 of the path share a machine (0 <= i < rg)
-    const int u = pf(i), w = pf(i + 1);
-    return !(u == w - 1 && !is_job_first(L, w));
-  };
-  for (int i0 = 0; i0 < rg; i0 += 32) {
-    const int i = i0 + lane;
-    bool take = false;
+  unsigned prevw = 0xffffffffu, curw = (unsigned)lds32(bits);
+  const int err = (len == 2 && (curw & 1u)) ? -9 : 0;
+  for (int k = 0; k <= kmax; ++k) {
+    const unsigned nextw = k < kmax ? (unsigned)lds32(bits + 4u * (k + 1)) : 0u;
+    const unsigned prev = (curw << 1) | (prevw >> 31), next = (curw >> 1) | (nextw << 31);
+    const int i = 32 * k + lane;
+    bool take = i < rg && (((curw & ~(prev & next)) >> lane) & 1u);
     int u = 0, w = 0;
-    if (i < rg && same(i)) {
-      u = pf(i); w = pf(i + 1);
-      if (i == 0) {
-        if (len < 3) err = -9; else take = !same(1);
-      } else if (!same(i - 1)) {
-        take = true;
-      } else if (i + 1 == rg) {
-        take = false;
-      } else {
-        take = !same(i + 1);
-      }
-      if (take && u == tabu0 && w == tabu1) take = false;
+    if (take) {
+      u = lds16(last - 2u * i);
+      w = lds16(last - 2u * i - 2u);
+      take = !(u == tabu0 && w == tabu1);
     }
     const unsigned bal = __ballot_sync(kFull, take);
-    if (take) emit(count + __popc(bal & ((1u << lane) - 1u)), u, w);
+    if (take) emit(count + __popc(bal & below), u, w);
     count += __popc(bal);
+    prevw = curw;
+    curw = nextw;
   }
-  err = __reduce_min_sync(kFull, err);
   return err < 0 ? err : count;
 }
 

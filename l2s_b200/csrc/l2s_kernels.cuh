@@ -313,6 +313,7 @@ struct StepArgs {
   uint32_t* rec;
   int rec_stride;          // words per record: 4 + pmax rounded up to a multiple of 16
   int rec_lines;           // write whole 64-byte lines (the words behind 4 + npairs are padding with stale contents)
+  int fast_sweep;          // CTA kernel: latency variant of the wavefront (few resident instances per SM)
   int incremental;         // CTA kernel: resume the sweeps from the cached evaluation st.fq (0: always sweep everything)
   // test introspection (l2s_export_state): evaluate only, no mutation
   int export_only;
@@ -635,6 +636,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   if (swap_r == 0) { tabu0 = a1; tabu1 = a0; } else if (swap_r < 0) status = swap_r;
   TLC(4);
   stage_wait_rest(s);
+  TLC(11);   // sentinels / cached evaluation landed
   // evaluation: forward sweep on warp 0, backward sweep on warp 1 (or both on warp 0 if the CTA has one warp).
   // With a cached evaluation nothing is swept when nothing moved, and after a swap only the part of the schedule
   // that can change (see resume_point): the rows resume behind their kept prefix (forward) / suffix (backward).
@@ -661,17 +663,20 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   if (sweep) {
     if (w == 0) {
       int last;
-      const bool ok = wavefront(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv);
+      const bool ok = a.fast_sweep ? wavefront_fast(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv)
+                                   : wavefront(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv);
       const int ms0 = __reduce_max_sync(kFull, last);
       if (lane == 0) { sh[3] = ms0; sh[4] = ok; }
       if (nw == 1) {
         int l2;
-        const bool ok2 = wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2);
+        const bool ok2 = a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2)
+                                      : wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2);
         if (lane == 0) sh[5] = ok2;
       }
     } else if (w == 1) {
       int l2;
-      const bool ok2 = wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv);
+      const bool ok2 = a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv)
+                                    : wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv);
       if (lane == 0) sh[5] = ok2;
     }
   } else if (tid == 0) {                   // nothing moved: the cached evaluation stands (fin[T] = makespan)
@@ -771,6 +776,14 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   __syncthreads();   // q is dead from here on: its storage holds msu and then the reversed critical path
   const uint32_t msu = q, rp = q + 2u * (uint32_t)n1;
   if (a.emc) link_pass<true>(L, s, msu, tid, nthr); else link_pass<false>(L, s, msu, tid, nthr);
+  if (tid == 0) { sts16(s.crit, 0); sts16(s.crit + 2u * (n + 1), 0); }                 // S and T map to S
+  if (w == nw - 1) { const int st0 = path_start(L, s, ms, lane); if (lane == 0) sh[7] = st0; }   // reads fin: before it is reused
+  __syncthreads();
+  // jump pointers for the path trace, in the (now dead) fin half of tq
+  const uint32_t jump2 = s.tq, jump4 = s.tq + 2u * (uint32_t)L.n1p;
+  square_map(jump2, s.crit, n1, tid, nthr);
+  __syncthreads();
+  square_map(jump4, jump2, n1, tid, nthr);
   __syncthreads();
   TLC(7);
   // the edge list is written by warps 1.. while warp 0 already traces the critical path (a single-warp CTA does
@@ -810,7 +823,7 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   }
   if (w != 0) return;
   __syncwarp();
-  const int len = trace_path(L, s, ms, lane, rp);
+  const int len = trace_path_jump(L, s, sh[7], lane, rp, jump2, jump4);
   TLC(8);
   if (a.ex_path) {
     for (int i = lane; i < len; i += 32) a.ex_path[(size_t)b * n + i] = lds16(rp + 2u * (len - 1 - i));
