@@ -29,7 +29,7 @@ inline int ru(long long x, int a) { return (int)((x + a - 1) / a * a); }
     }                                                                                             \
   } while (0)
 
-Layout make_layout(int n_j, int n_m, bool stage_durw = false, int pmax = 0) {
+Layout make_layout(int n_j, int n_m, bool stage_durw = false, int pmax = 0, bool decouple = false) {
   Layout L;
   memset(&L, 0, sizeof(L));
   L.n_j = n_j;
@@ -67,6 +67,16 @@ Layout make_layout(int n_j, int n_m, bool stage_durw = false, int pmax = 0) {
       L.off_bits = off;
       off += bits_bytes;
     }
+  }
+  // latency regime of the CTA kernel: shared memory is plentiful, so the arrays that otherwise overlay the dead halves
+  // of tq get regions of their own and the outputs can be written while warp 0 traces the critical path
+  L.off_msu = L.off_rp = L.off_j2 = L.off_j4 = -1;
+  if (decouple) {
+    off = ru(off, 16);
+    L.off_msu = off; off += L.node_stride * 2;
+    L.off_j2 = off;  off += L.node_stride * 2;
+    L.off_j4 = off;  off += L.node_stride * 2;
+    L.off_rp = off;  off += ru(L.n * 2, 16);
   }
   L.magic_nm = (unsigned)((1ull << 32) / (unsigned)n_m) + 1u;
   L.bytes = ru(off, 16);
@@ -268,6 +278,14 @@ static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int 
     // latency variant; many: the schedulers are saturated by sweep instructions -> lean variant (l2s_device.cuh)
     h->fast_sweep = h->cta_warps > 0 && resident <= 4;
     if (const char* e = getenv("L2S_FAST_SWEEP")) h->fast_sweep = atoi(e) != 0;
+    // ... and shared memory is plentiful: decoupled regions (make_layout) if the resident instances still fit
+    bool decouple = h->cta_warps > 1 && resident <= 4;
+    if (const char* e = getenv("L2S_DECOUPLE")) decouple = h->cta_warps > 1 && atoi(e) != 0;
+    if (decouple) {
+      const Layout L2 = make_layout(n_j, n_m, false, pmax, true);
+      if ((long long)(kSmemPerSm / ((size_t)L2.bytes + kSmemCtaReserve)) >= resident && (size_t)L2.bytes + 1024 <= kSmemPerCtaMax)
+        h->L = L2;
+    }
   }
   CU(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax - 1024));   // it also has static shared memory
   CU(cudaFuncSetAttribute(step_kernel_cta, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -732,12 +750,31 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   a.off_heads = off; off += 64;
   a.off_bar = off;   off += 16;
   a.bytes = ru(off, 16);
-  const int W = pick_warps(a.bytes, 4);
-  if (!W) return L2S_ERR_UNSUPPORTED_SHAPE;
+  // warp per graph while at least 16 graphs fit an SM, else one CTA per graph (coo_eval_kernel_cta)
+  const bool cta = (long long)(kSmemPerSm / ((size_t)a.bytes + kSmemCtaReserve)) < 16 || getenv("L2S_EVAL_CTA") != nullptr;
+  int W = 0, cta_warps = 0;
+  if (cta) {
+    a.off_anchor = a.bytes;
+    a.bytes = ru((long long)a.bytes + 2ll * n_m * ((n_j + 3) / 4), 16);
+    if ((size_t)a.bytes + 1024 > kSmemPerCtaMax) return L2S_ERR_UNSUPPORTED_SHAPE;
+    const long long per_sm = (long long)(kSmemPerSm / ((size_t)a.bytes + kSmemCtaReserve));
+    long long resident = (batch + 147) / 148;
+    if (resident > per_sm) resident = per_sm;
+    if (resident < 1) resident = 1;
+    cta_warps = resident >= 12 ? 2 : resident >= 5 ? 4 : 8;
+    if (const char* e = getenv("L2S_EVAL_CTA")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) cta_warps = v; }
+    a.fast_sweep = resident <= 4;
+    if (const char* e = getenv("L2S_FAST_SWEEP")) a.fast_sweep = atoi(e) != 0;
+  } else {
+    W = pick_warps(a.bytes, 4);
+    if (!W) return L2S_ERR_UNSUPPORTED_SHAPE;
+  }
   static bool attr_set[64] = {false};
   if (device >= 0 && device < 64 && !attr_set[device]) {
     CU(cudaFuncSetAttribute(coo_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax));
     CU(cudaFuncSetAttribute(coo_eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(coo_eval_kernel_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerCtaMax - 1024));
+    CU(cudaFuncSetAttribute(coo_eval_kernel_cta, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[device] = true;
   }
   if (!workspace_is_clean) CU(cudaMemsetAsync(workspace, 0, links + 16, s));
@@ -755,7 +792,8 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   if (blocks < 1) blocks = 1;
   coo_ingest_kernel<<<(unsigned)blocks, 256, 0, s>>>(g);
   CU(cudaGetLastError());
-  coo_eval_kernel<<<(unsigned)((batch + W - 1) / W), W * 32, (size_t)W * a.bytes, s>>>(a);
+  if (cta) coo_eval_kernel_cta<<<(unsigned)batch, cta_warps * 32, (size_t)a.bytes, s>>>(a);
+  else coo_eval_kernel<<<(unsigned)((batch + W - 1) / W), W * 32, (size_t)W * a.bytes, s>>>(a);
   CU(cudaGetLastError());
   return L2S_OK;
 }

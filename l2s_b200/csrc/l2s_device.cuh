@@ -59,6 +59,8 @@ struct Layout {
   int off_tq, off_walk, off_crit, off_misc;
   int off_durw;          // >= 0: static node words staged in shared memory (small instances); -1: read from HBM
   int off_rec;           // staging of the host record (4 + pmax words): overlays crit when that is large enough
+  int off_msu;           // >= 0 (CTA kernel, few resident instances): own regions for the machine successors, the path
+  int off_rp, off_j2, off_j4;   //   and the jump maps, so that feature / edge output overlaps the path trace; -1: overlays
   int off_bits;          // n5_moves scratch (one bit per path position): in crit, behind the record staging if that overlays it
   unsigned magic_nm;     // floor(2^32 / n_m) + 1: (x mod n_m) by multiply-shift for x < 2^16
   int bytes;             // per instance (step kernel)

@@ -593,16 +593,20 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   // for the feature loop NOW (clamped index: no select that would wait for the data), so that the loads are in
   // flight during staging and the sweeps instead of being a chain of dependent global-load latencies inside that
   // loop (measured at 100x20: 9-11 us -> 1-3 us)
-  constexpr int kPairRegs = 8;
+  constexpr int kPairRegs = 9;
   const uint16_t* gdurw = a.st.durw + (size_t)b * L.node_stride;
   // fast feature path: both divisors pass the one-correction test, even node count (8-byte aligned rows), and a
   // thread's share of node-word PAIRS fits the registers
-  const bool x_fast = a.x && a.div_high == 1 && a.div_fea == 1 && !(n1 & 1) && ((n1 >> 1) + nthr - 1) / nthr <= kPairRegs;
+  // decoupled regions (latency regime, see make_layout): warp 0 goes straight from the link pass to the path trace and
+  // the move set while warps 1.. write the features and the edge list; otherwise all threads write the features first
+  const bool decoupled = L.off_msu >= 0 && nw > 1;
+  const int xt = decoupled ? tid - 32 : tid, xn = decoupled ? nthr - 32 : nthr;     // feature-writer index / count
+  const bool x_fast = a.x && a.div_high == 1 && a.div_fea == 1 && !(n1 & 1) && ((n1 >> 1) + xn - 1) / xn <= kPairRegs;
   unsigned dpair[kPairRegs];
-  if (x_fast) {
+  if (x_fast && xt >= 0) {
 #pragma unroll
     for (int k = 0; k < kPairRegs; ++k)
-      dpair[k] = __ldg(reinterpret_cast<const unsigned*>(gdurw) + min(tid + k * nthr, (n1 >> 1) - 1));
+      dpair[k] = __ldg(reinterpret_cast<const unsigned*>(gdurw) + min(xt + k * xn, (n1 >> 1) - 1));
   }
   // incremental re-evaluation: the completion times / tails of the previous evaluation come back from HBM
   // (one more bulk copy on the second barrier) instead of "pending" sentinels
@@ -719,73 +723,79 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
     for (int i = tid; i < L.n1p / 2; i += nthr) g[i] = lds128(s.tq + 16u * i);
     if (tid == 0) a.st.evalid[b] = 1;
   }
-  if (a.x) {
-    float* xo = a.x + (size_t)b * n1 * 3;
-    const float fms = (float)ms;
-    if (x_fast) {
-      // two adjacent nodes per thread: 64-bit shared loads, 64-bit global stores, one FMA residual correction
-      const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
-      float2* const xb = reinterpret_cast<float2*>(xo);
-#pragma unroll
-      for (int k = 0; k < kPairRegs; ++k) {
-        const int p = tid + k * nthr;
-        if (p < (n1 >> 1)) {
-          const unsigned dw = dpair[k];
-          const int2 f = lds64(fin + 8u * p), t = lds64(q + 8u * p);
-          const int d0 = (int)(dw & kDurMask), d1 = (int)((dw >> 16) & kDurMask);
-          const float fd0 = (float)d0, fe0 = (float)(f.x - d0), fl0 = fms - (float)t.x;
-          const float fd1 = (float)d1, fe1 = (float)(f.y - d1), fl1 = fms - (float)t.y;
-          const float q00 = __fmul_rn(fd0, rh), q01 = __fmul_rn(fe0, rf), q02 = __fmul_rn(fl0, rf);
-          const float q10 = __fmul_rn(fd1, rh), q11 = __fmul_rn(fe1, rf), q12 = __fmul_rn(fl1, rf);
-          float2* const xo2 = xb + 3 * p;
-          xo2[0] = make_float2(__fmaf_rn(__fmaf_rn(-ch, q00, fd0), rh, q00), __fmaf_rn(__fmaf_rn(-cf, q01, fe0), rf, q01));
-          xo2[1] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q02, fl0), rf, q02), __fmaf_rn(__fmaf_rn(-ch, q10, fd1), rh, q10));
-          xo2[2] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q11, fe1), rf, q11), __fmaf_rn(__fmaf_rn(-cf, q12, fl1), rf, q12));
+  auto write_features = [&]() {
+    if (a.x) {
+      float* xo = a.x + (size_t)b * n1 * 3;
+      const float fms = (float)ms;
+      if (x_fast) {
+        // two adjacent nodes per thread: 64-bit shared loads, 64-bit global stores, one FMA residual correction
+        const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
+        float2* const xb = reinterpret_cast<float2*>(xo);
+  #pragma unroll
+        for (int k = 0; k < kPairRegs; ++k) {
+          const int p = xt + k * xn;
+          if (p < (n1 >> 1)) {
+            const unsigned dw = dpair[k];
+            const int2 f = lds64(fin + 8u * p), t = lds64(q + 8u * p);
+            const int d0 = (int)(dw & kDurMask), d1 = (int)((dw >> 16) & kDurMask);
+            const float fd0 = (float)d0, fe0 = (float)(f.x - d0), fl0 = fms - (float)t.x;
+            const float fd1 = (float)d1, fe1 = (float)(f.y - d1), fl1 = fms - (float)t.y;
+            const float q00 = __fmul_rn(fd0, rh), q01 = __fmul_rn(fe0, rf), q02 = __fmul_rn(fl0, rf);
+            const float q10 = __fmul_rn(fd1, rh), q11 = __fmul_rn(fe1, rf), q12 = __fmul_rn(fl1, rf);
+            float2* const xo2 = xb + 3 * p;
+            xo2[0] = make_float2(__fmaf_rn(__fmaf_rn(-ch, q00, fd0), rh, q00), __fmaf_rn(__fmaf_rn(-cf, q01, fe0), rf, q01));
+            xo2[1] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q02, fl0), rf, q02), __fmaf_rn(__fmaf_rn(-ch, q10, fd1), rh, q10));
+            xo2[2] = make_float2(__fmaf_rn(__fmaf_rn(-cf, q11, fe1), rf, q11), __fmaf_rn(__fmaf_rn(-cf, q12, fl1), rf, q12));
+          }
+        }
+      } else if (a.div_high == 1 && a.div_fea == 1) {   // odd node count or a very large instance: node by node
+        const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
+  #pragma unroll 4
+        for (int i = xt; i < n1; i += xn) {
+          const int d = __ldg(gdurw + i) & kDurMask;
+          const float fd = (float)d, fe = (float)(lds32(fin + 4u * i) - d), fl = fms - (float)lds32(q + 4u * i);
+          const float q0 = __fmul_rn(fd, rh), q1 = __fmul_rn(fe, rf), q2 = __fmul_rn(fl, rf);
+          xo[3 * i] = __fmaf_rn(__fmaf_rn(-ch, q0, fd), rh, q0);
+          xo[3 * i + 1] = __fmaf_rn(__fmaf_rn(-cf, q1, fe), rf, q1);
+          xo[3 * i + 2] = __fmaf_rn(__fmaf_rn(-cf, q2, fl), rf, q2);
+        }
+      } else {
+  #pragma unroll 4
+        for (int i = xt; i < n1; i += xn) {
+          const int d = __ldg(gdurw + i) & kDurMask;
+          const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
+          xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
+          xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
+          xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
         }
       }
-    } else if (a.div_high == 1 && a.div_fea == 1) {   // odd node count or a very large instance: node by node
-      const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
-#pragma unroll 4
-      for (int i = tid; i < n1; i += nthr) {
+    }
+    if (a.ex_est) {
+      for (int i = xt; i < n1; i += xn) {
         const int d = __ldg(gdurw + i) & kDurMask;
-        const float fd = (float)d, fe = (float)(lds32(fin + 4u * i) - d), fl = fms - (float)lds32(q + 4u * i);
-        const float q0 = __fmul_rn(fd, rh), q1 = __fmul_rn(fe, rf), q2 = __fmul_rn(fl, rf);
-        xo[3 * i] = __fmaf_rn(__fmaf_rn(-ch, q0, fd), rh, q0);
-        xo[3 * i + 1] = __fmaf_rn(__fmaf_rn(-cf, q1, fe), rf, q1);
-        xo[3 * i + 2] = __fmaf_rn(__fmaf_rn(-cf, q2, fl), rf, q2);
-      }
-    } else {
-#pragma unroll 4
-      for (int i = tid; i < n1; i += nthr) {
-        const int d = __ldg(gdurw + i) & kDurMask;
-        const int f = lds32(fin + 4u * i), t = lds32(q + 4u * i);
-        xo[3 * i] = div_rn((float)d, a.high, a.r_high, a.div_high);
-        xo[3 * i + 1] = div_rn((float)(f - d), a.fea, a.r_fea, a.div_fea);
-        xo[3 * i + 2] = div_rn(fms - (float)t, a.fea, a.r_fea, a.div_fea);
+        a.ex_est[(size_t)b * n1 + i] = lds32(fin + 4u * i) - d;
+        a.ex_lst[(size_t)b * n1 + i] = ms - lds32(q + 4u * i);
       }
     }
-  }
-  if (a.ex_est) {
-    for (int i = tid; i < n1; i += nthr) {
-      const int d = __ldg(gdurw + i) & kDurMask;
-      a.ex_est[(size_t)b * n1 + i] = lds32(fin + 4u * i) - d;
-      a.ex_lst[(size_t)b * n1 + i] = ms - lds32(q + 4u * i);
-    }
-  }
+  };
+  if (!decoupled) write_features();
   TLC(6);
-  __syncthreads();   // q is dead from here on: its storage holds msu and then the reversed critical path
-  const uint32_t msu = q, rp = q + 2u * (uint32_t)n1;
+  __syncthreads();   // (overlay mode) q is dead from here on: its storage holds msu and then the reversed critical path
+  const uint32_t base0 = smem_addr(smem_step);
+  const uint32_t msu = decoupled ? base0 + L.off_msu : q, rp = decoupled ? base0 + L.off_rp : q + 2u * (uint32_t)n1;
   if (a.emc) link_pass<true>(L, s, msu, tid, nthr); else link_pass<false>(L, s, msu, tid, nthr);
   if (tid == 0) { sts16(s.crit, 0); sts16(s.crit + 2u * (n + 1), 0); }                 // S and T map to S
   if (w == nw - 1) { const int st0 = path_start(L, s, ms, lane); if (lane == 0) sh[7] = st0; }   // reads fin: before it is reused
   __syncthreads();
-  // jump pointers for the path trace, in the (now dead) fin half of tq
-  const uint32_t jump2 = s.tq, jump4 = s.tq + 2u * (uint32_t)L.n1p;
+  // jump pointers for the path trace, in the (now dead) fin half of tq unless they have regions of their own
+  const uint32_t jump2 = decoupled ? base0 + L.off_j2 : s.tq;
+  const uint32_t jump4 = decoupled ? base0 + L.off_j4 : s.tq + 2u * (uint32_t)L.n1p;
   square_map(jump2, s.crit, n1, tid, nthr);
   __syncthreads();
   square_map(jump4, jump2, n1, tid, nthr);
   __syncthreads();
   TLC(7);
+  if (decoupled && w > 0) write_features();
   // the edge list is written by warps 1.. while warp 0 already traces the critical path (a single-warp CTA does
   // both in turn); msu and rp are disjoint parts of the dead q half
   const int ew = nw > 1 ? nw - 1 : 1, myw = nw > 1 ? w - 1 : 0;
@@ -1202,6 +1212,8 @@ struct CooEvalArgs {
   float* ms;
   int bytes;           // smem per graph
   int off_durw, off_succ, off_heads, off_bar;
+  int off_anchor;      // CTA kernel: uint16 [n_m][ceil(n_j/4)] chain anchors
+  int fast_sweep;      // CTA kernel: latency variant of the wavefront
   long long expect_conj;
 };
 
@@ -1366,6 +1378,190 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   }
   if (lane == 0) a.ms[b] = (float)ms;
   TL(8); TL(1);
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// The same evaluator for LARGE graphs (fewer than 16 fit an SM, so a warp per graph would leave the SM almost empty:
+// 3 warps at 150x25): one CTA of 4-8 warps per graph.  Staging, head finding, the duration conversion and the outputs
+// are spread over all threads; the machine chains are turned into walk rows with the jump-pointer trick of the step
+// kernel's path trace (successor map squared twice, one lane per chain drops an anchor every fourth position, all
+// threads fill the three operations behind every anchor); warp 0 sweeps forward while warp 1 sweeps backward.
+// Shared memory: the warp kernel's regions plus the anchors (uint16 [n_m][ceil(n_j/4)]).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) coo_eval_kernel_cta(const __grid_constant__ CooEvalArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_coo[];
+  __shared__ int sh[8];   // 0: heads, 1: machine arcs, 2: bad, 3: makespan, 4: fwd ok, 5: bwd ok, 6: qs
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+  const long long b = blockIdx.x;
+  const Layout& L = a.L;
+  const uint32_t base = smem_addr(smem_coo);
+  const Inst s = inst_view(L, base);
+  const uint32_t succ = base + a.off_succ, heads = base + a.off_heads, durw = base + a.off_durw;
+  const uint32_t anchors = base + a.off_anchor;
+  const int n = L.n, n1 = L.n1, n_m = L.n_m, n_j = L.n_j;
+  const int n4 = (n_j + 3) >> 2;                         // anchors per chain
+  if (tid < 8) sh[tid] = 0;
+  if (b == 0 && tid == 0) {
+    if (*a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
+    *a.ws.conj_count = 0ull;   // the workspace is handed back zero-filled (see l2s_eval_coo)
+  }
+  const uint32_t bar = base + a.off_bar, bar2 = bar + 8u;
+  if (tid == 0) {
+    const uint32_t sbytes = (uint32_t)L.node_stride * 2u;
+    mbar_init(bar, 1);
+    mbar_init(bar2, 1);
+    mbar_expect_tx(bar, sbytes);
+    bulk_g2s(succ, a.ws.msucc + b * L.node_stride, sbytes, bar);
+    if (a.dur_tma) {
+      mbar_expect_tx(bar2, (uint32_t)n1 * 8u);
+      bulk_g2s(s.tq, reinterpret_cast<const long long*>(a.duration) + b * n1, (uint32_t)n1 * 8u, bar2);
+    }
+  }
+  int bad = 0;
+  auto node_word = [&](int i, long long d) -> int {     // node word of node i from its duration d
+    if (d < 0 || d > kDurMax) { bad = 1; d = 0; }
+    int word = (int)d;
+    if (i >= 1 && i <= n) {
+      const int pos = (i - 1) % n_m;
+      word |= (pos == 0 ? kFirstFlag : 0) | (pos == n_m - 1 ? kLastFlag : 0);
+    } else if (d != 0) {
+      bad = 1;
+    }
+    return word;
+  };
+  if (!a.dur_tma) {
+    for (int i = tid; i < n1; i += nthr) {
+      const long long d = a.dur_i64 ? reinterpret_cast<const long long*>(a.duration)[b * n1 + i]
+                                    : (long long)reinterpret_cast<const int32_t*>(a.duration)[b * n1 + i];
+      sts16(durw + 2u * i, node_word(i, d));
+    }
+  }
+  // flag bytes (in the still unused walk words): 1 = somebody points to this node
+  const uint32_t flags = s.walk;
+  for (int i = tid; i < (n1 + 15) >> 4; i += nthr) sts128(flags + 16u * i, make_uint4(0u, 0u, 0u, 0u));
+  __syncthreads();                                         // barriers initialised, flags cleared
+  mbar_wait(bar, 0);
+  {   // the successors are in shared memory: hand the row of the workspace back zero-filled
+    uint4* grow = reinterpret_cast<uint4*>(a.ws.msucc + b * L.node_stride);
+    for (int i = tid; i < L.node_stride / 8; i += nthr) grow[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  int narc = 0;
+  for (int v = 1 + tid; v <= n; v += nthr) {
+    const int sc = lds16(succ + 2u * v);
+    if (sc) { sts8(flags + (uint32_t)sc, 1); ++narc; }
+  }
+  narc = __reduce_add_sync(kFull, narc);
+  if (lane == 0 && narc) atomicAdd(&sh[1], narc);
+  if (a.dur_tma) {   // the raw durations have landed in tq by now: convert them
+    mbar_wait(bar2, 0);
+    for (int i = tid; i < n1; i += nthr) {
+      const int2 dd = lds64(s.tq + 8u * i);
+      sts16(durw + 2u * i, node_word(i, (long long)(((unsigned long long)(unsigned)dd.y << 32) | (unsigned)dd.x)));
+    }
+  }
+  __syncthreads();                                         // flags complete, tq free
+  // heads = operations nobody points to (any order: a chain may take any walk row); successor map squared twice
+  const uint32_t s2 = s.tq, s4 = s.tq + 2u * (uint32_t)L.n1p;
+  for (int v = 1 + tid; v <= n; v += nthr) {
+    if (lds8(flags + (uint32_t)v) == 0) {
+      const int slot = atomicAdd(&sh[0], 1);
+      if (slot < 32) sts16(heads + 2u * slot, v);
+    }
+  }
+  square_map(s2, succ, n1, tid, nthr);
+  if (__syncthreads_or(bad)) {
+    if (tid == 0) atomicCAS(a.ws.flag, 0, -6);
+    return;
+  }
+  square_map(s4, s2, n1, tid, nthr);
+  // a complete selection has exactly n_m machine chains of n_j operations: n_m heads, n - n_m machine arcs
+  if (sh[0] != n_m || sh[1] != n - n_m) {
+    if (tid == 0) atomicCAS(a.ws.flag, 0, -5);
+    return;
+  }
+  __syncthreads();
+  // one lane per chain follows the fourth-successor map: an anchor every fourth operation
+  if (w == 0 && lane < n_m) {
+    int v = lds16(heads + 2u * lane), k = 0;
+    while (v != 0 && k < n4) {
+      sts16(anchors + 2u * (uint32_t)(lane * n4 + k), v);
+      v = lds16(s4 + 2u * v);
+      ++k;
+    }
+    if (k != n4 || v != 0) sh[2] = 1;                       // shorter or longer than n_j (or a cycle)
+  }
+  __syncthreads();
+  if (sh[2]) {
+    if (tid == 0) atomicCAS(a.ws.flag, 0, -5);
+    return;
+  }
+  // all threads: the walk words of every anchor and of the (up to) three operations behind it
+  int chain_bad = 0;
+  for (int idx = tid; idx < n_m * n4; idx += nthr) {
+    const int k = idx / n4, i = idx - k * n4;
+    const int v0 = lds16(anchors + 2u * idx);
+    const int v1 = lds16(succ + 2u * v0), v2 = lds16(s2 + 2u * v0);
+    const int v3 = lds16(succ + 2u * v2);
+    const int vs[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pos = 4 * i + j;
+      if (pos < n_j) {
+        if (vs[j] == 0) chain_bad = 1;
+        else sts32(s.walk + 4u * (uint32_t)(k * n_j + pos), (int)make_walk(vs[j], lds16(durw + 2u * vs[j]), false, pos == n_j - 1));
+      } else if (vs[j] != 0) {
+        chain_bad = 1;
+      }
+    }
+  }
+  if (__syncthreads_or(chain_bad)) {                        // (also: walk rows complete, the jump maps are dead)
+    if (tid == 0) atomicCAS(a.ws.flag, 0, -5);
+    return;
+  }
+  fill_pending(L, s, tid, true, nthr);
+  __syncthreads();
+  __syncwarp();
+  if (w == 0) {
+    int last;
+    const bool ok = a.fast_sweep ? wavefront_fast(L, s, lane, 0, lane < n_m, last) : wavefront(L, s, lane, 0, lane < n_m, last);
+    const int ms0 = __reduce_max_sync(kFull, last);
+    if (lane == 0) { sh[3] = ms0; sh[4] = ok; }
+  } else if (w == 1) {
+    int l2;
+    const bool ok2 = a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < n_m, l2) : wavefront(L, s, lane, 1, lane < n_m, l2);
+    if (lane == 0) sh[5] = ok2;
+  }
+  __syncthreads();
+  const int ms = sh[3];
+  if (!sh[4] || !sh[5]) {
+    if (tid == 0) atomicCAS(a.ws.flag, 0, -5);
+    return;
+  }
+  const uint32_t fin = s.tq, q = s.tq + 4u * L.n1p;
+  {
+    int qs = 0;
+    for (int j = tid; j < n_j; j += nthr) qs = max(qs, lds32(q + 4u * (j * n_m + 1)));
+    qs = __reduce_max_sync(kFull, qs);
+    if (lane == 0 && qs > 0) atomicMax(&sh[6], qs);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    sts32(fin, 0);
+    sts32(q, sh[6]);
+    sts32(fin + 4u * (n + 1), ms);
+    sts32(q + 4u * (n + 1), 0);
+    a.ms[b] = (float)ms;
+  }
+  __syncthreads();
+  float* eo = a.est + b * n1;
+  float* lo = a.lst + b * n1;
+  for (int i = tid; i < n1; i += nthr) {
+    const int d = lds16(durw + 2u * i) & kDurMask;
+    eo[i] = (float)(lds32(fin + 4u * i) - d);
+    lo[i] = (float)(ms - lds32(q + 4u * i));
+  }
+  (void)nw;
 }
 
 }  // namespace l2s

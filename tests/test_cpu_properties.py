@@ -81,3 +81,41 @@ def test_host_record_macros_match_the_python_decoding(tmp_path):
         assert [int(v) for v in out[i].split()] == [int(npairs[i]), int(done[i]), int(status[i])]
     from l2s_b200 import _capi
     assert int(out[len(words)]) == _capi.REC_HEADER_WORDS
+
+
+def test_move_lists_behave_like_the_reference_nested_lists():
+    """`MoveLists` (the lazy `feasible_actions` of JsspN5.step) against plain nested lists built from the same host
+    records: len, indexing (incl. negative / slices), iteration, equality both ways, [[0, 0]] for instances without
+    moves, and the numpy view `arrays()`; the C glue and the pure-Python route must agree."""
+    import numpy as np
+    from l2s_b200 import _capi
+    from l2s_b200.environment import MoveLists
+    rng = np.random.RandomState(0)
+    B, pmax = 37, 12
+    stride = 16
+    rec = np.zeros((B, stride), dtype=np.uint32)
+    want = []
+    for b in range(B):
+        c = 0 if b % 5 == 0 else int(rng.randint(1, pmax + 1))
+        pairs = rng.randint(1, 400, size=(c, 2))
+        rec[b, 0] = c | ((1 << 16) if c == 0 else 0)
+        rec[b, 4:4 + c] = pairs[:, 0] | (pairs[:, 1] << 16)
+        rec[b, 4 + c:] = 0xdeadbeef                     # stale words behind the valid prefix must be ignored
+        want.append(pairs.tolist() if c else [[0, 0]])
+    fa = MoveLists(rec.copy())
+    assert len(fa) == B and fa[3] == want[3] and fa[-1] == want[-1] and fa[0] == [[0, 0]]
+    assert len(fa[7]) == len(want[7]) and fa[7][0][1] == want[7][0][1]
+    assert fa == want and want == fa.tolist() and not (fa != want)
+    assert [f for f in fa] == want and fa[2:5] == want[2:5]
+    assert MoveLists(rec.copy()) == fa
+    with pytest.raises(IndexError):
+        fa[B]
+    pairs, cnt = fa.arrays()
+    assert pairs.shape == (B, stride - 4, 2) and cnt.tolist() == [0 if w == [[0, 0]] else len(w) for w in want]
+    for b in range(B):
+        assert pairs[b, :cnt[b]].tolist() == (want[b] if cnt[b] else [])
+        assert not pairs[b, cnt[b]:].any()
+    lazy = MoveLists(rec.copy())
+    assert [lazy._row(b) for b in range(B)] == want       # pure-Python route == C glue route
+    if _capi.pylists() is not None:
+        assert lazy.tolist() == want

@@ -340,3 +340,25 @@ def test_plist_reset_matches_reference_golden():
         p, c = _pairs_from_fa(fa, 32)
         assert np.array_equal(p, g["pairs"][k]) and np.array_equal(c, g["npairs"][k])
     assert np.array_equal(state[0].cpu().numpy(), g["x_last"])
+
+
+@pytest.mark.parametrize("cta_warps", ["2", "4", "8"])
+def test_evaluator_cta_kernel_matches_reference(cta_warps, monkeypatch):
+    """The CTA-per-graph evaluator kernel (the default for graphs of which fewer than 16 fit an SM) forced onto the
+    small golden graphs with 2 / 4 / 8 warps per graph, lean and latency sweep: same est / lst / makespan as the
+    reference's Evaluator.forward."""
+    from l2s_b200 import Evaluator
+    g = np.load(os.path.join(GOLDEN, "eval_coo.npz"))
+    monkeypatch.setenv("L2S_EVAL_CTA", cta_warps)
+    for fast in ("0", "1"):
+        monkeypatch.setenv("L2S_FAST_SWEEP", fast)
+        ev = Evaluator()
+        for tag in ("6x4", "10x10", "20x15", "30x20"):
+            n_j, n_m, B = [int(v) for v in g["shape_" + tag]]
+            ei = torch.from_numpy(g["ei_" + tag]).cuda()
+            for dt in (torch.int32, torch.int64):
+                dur = torch.from_numpy(g["dur_" + tag]).to(dt).cuda()
+                est, lst, ms = ev.forward(ei, dur, n_j, n_m)
+                assert np.array_equal(est.cpu().numpy(), g["est_" + tag]), (tag, fast)
+                assert np.array_equal(lst.cpu().numpy(), g["lst_" + tag]), (tag, fast)
+                assert np.array_equal(ms.cpu().numpy(), g["ms_" + tag]), (tag, fast)
