@@ -750,8 +750,13 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   a.off_heads = off; off += 64;
   a.off_bar = off;   off += 16;
   a.bytes = ru(off, 16);
-  // warp per graph while at least 16 graphs fit an SM, else one CTA per graph (coo_eval_kernel_cta)
-  const bool cta = (long long)(kSmemPerSm / ((size_t)a.bytes + kSmemCtaReserve)) < 16 || getenv("L2S_EVAL_CTA") != nullptr;
+  // warp per graph while at least 16 graphs fit an SM, else one CTA per graph (coo_eval_kernel_cta) -- except for the
+  // band where 4-7 graphs fit and the batch keeps them all busy (100x20 at batch 1024: warp kernel 52 us, CTA kernel
+  // 56-69 us; measured table in profiles/README_r2.md)
+  const long long fits_warp = (long long)(kSmemPerSm / ((size_t)a.bytes + kSmemCtaReserve));
+  const long long busy_warp = fits_warp < (batch + 147) / 148 ? fits_warp : (batch + 147) / 148;
+  bool cta = fits_warp < 16 && !(fits_warp >= 4 && fits_warp < 8 && busy_warp > 2);
+  if (const char* e = getenv("L2S_EVAL_CTA")) cta = atoi(e) != 0;     // experiments / tests: 0 = warp kernel, 2|4|8 = CTA kernel
   int W = 0, cta_warps = 0;
   if (cta) {
     a.off_anchor = a.bytes;
