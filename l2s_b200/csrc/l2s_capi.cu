@@ -797,8 +797,30 @@ int l2s_eval_coo(const int64_t* edge_index, int64_t n_edges, const void* duratio
   if (blocks < 1) blocks = 1;
   coo_ingest_kernel<<<(unsigned)blocks, 256, 0, s>>>(g);
   CU(cudaGetLastError());
-  if (cta) coo_eval_kernel_cta<<<(unsigned)batch, cta_warps * 32, (size_t)a.bytes, s>>>(a);
-  else coo_eval_kernel<<<(unsigned)((batch + W - 1) / W), W * 32, (size_t)W * a.bytes, s>>>(a);
+  {
+    // programmatic dependent launch: the per-graph kernel's prologue overlaps the tail of the ingest kernel
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("L2S_EVAL_PDL"); pdl = e ? atoi(e) != 0 : 1; }
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (cta) {
+      cfg.gridDim = dim3((unsigned)batch);
+      cfg.blockDim = dim3((unsigned)cta_warps * 32);
+      cfg.dynamicSmemBytes = (size_t)a.bytes;
+      CU(cudaLaunchKernelEx(&cfg, coo_eval_kernel_cta, a));
+    } else {
+      cfg.gridDim = dim3((unsigned)((batch + W - 1) / W));
+      cfg.blockDim = dim3((unsigned)W * 32);
+      cfg.dynamicSmemBytes = (size_t)W * a.bytes;
+      CU(cudaLaunchKernelEx(&cfg, coo_eval_kernel, a));
+    }
+  }
   CU(cudaGetLastError());
   return L2S_OK;
 }

@@ -1154,6 +1154,10 @@ __device__ __forceinline__ int coo_edge(const CooIngestArgs& a, long long u64, l
 // are 16-byte aligned when E is even; otherwise (or for a misaligned view) every thread takes single edges.
 constexpr int kIngestTrips = 4;
 __global__ void __launch_bounds__(256) coo_ingest_kernel(const __grid_constant__ CooIngestArgs a) {
+  // programmatic dependent launch: the per-graph kernel may be scheduled as soon as every CTA of this grid has started
+  // (its prologue -- barrier set-up, the bulk copy of the durations -- does not depend on this kernel; it waits with
+  // griddepcontrol.wait before it touches the successor array)
+  asm volatile("griddepcontrol.launch_dependents;");
   int conj = 0, bad = 0;
   const unsigned E = (unsigned)a.E;
   const unsigned tid0 = blockIdx.x * (256u * kIngestTrips) + threadIdx.x;
@@ -1229,26 +1233,30 @@ __global__ void __launch_bounds__(128, 8) coo_eval_kernel(const __grid_constant_
   const uint32_t durw = base + a.off_durw;                               // uint16 [node_stride] node words
   const int n = L.n, n1 = L.n1, n_m = L.n_m, n_j = L.n_j;
   TL(0); TL(2);
-  if (b == 0 && lane == 0) {
-    if (*a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
-    *a.ws.conj_count = 0ull;   // the workspace is handed back zero-filled (see l2s_eval_coo)
-  }
 
   // stage: machine successors (and, for the plain path, the "pending" sentinels) by TMA bulk copies issued by one
   // lane.  Durations: when the int64 rows are 16-byte aligned they are bulk-copied RAW into tq (8*n1 <= 8*n1p bytes)
   // on a second barrier and converted after the chain heads have been found, so that the largest input of the call
   // is in flight while the warp works; otherwise they are loaded and converted here.
+  // Everything up to griddepcontrol.wait is independent of the ingest kernel and may overlap its tail.
   const uint32_t bar = base + a.off_bar, bar2 = bar + 8u;
   if (lane == 0) {
-    const uint32_t sbytes = (uint32_t)L.node_stride * 2u;
     mbar_init(bar, 1);
     mbar_init(bar2, 1);
-    mbar_expect_tx(bar, sbytes);
-    bulk_g2s(succ, a.ws.msucc + b * L.node_stride, sbytes, bar);
     if (a.dur_tma) {
       mbar_expect_tx(bar2, (uint32_t)n1 * 8u);
       bulk_g2s(s.tq, reinterpret_cast<const long long*>(a.duration) + b * n1, (uint32_t)n1 * 8u, bar2);
     }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (b == 0 && lane == 0) {
+    if (*a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
+    *a.ws.conj_count = 0ull;   // the workspace is handed back zero-filled (see l2s_eval_coo)
+  }
+  if (lane == 0) {
+    const uint32_t sbytes = (uint32_t)L.node_stride * 2u;
+    mbar_expect_tx(bar, sbytes);
+    bulk_g2s(succ, a.ws.msucc + b * L.node_stride, sbytes, bar);
   }
   if (!a.dur_tma) fill_pending(L, s, lane, true);   // tq is free: "pending" sentinels right away
   int bad = 0;
@@ -1402,21 +1410,24 @@ __global__ void __launch_bounds__(256) coo_eval_kernel_cta(const __grid_constant
   const int n = L.n, n1 = L.n1, n_m = L.n_m, n_j = L.n_j;
   const int n4 = (n_j + 3) >> 2;                         // anchors per chain
   if (tid < 8) sh[tid] = 0;
-  if (b == 0 && tid == 0) {
-    if (*a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
-    *a.ws.conj_count = 0ull;   // the workspace is handed back zero-filled (see l2s_eval_coo)
-  }
   const uint32_t bar = base + a.off_bar, bar2 = bar + 8u;
   if (tid == 0) {
-    const uint32_t sbytes = (uint32_t)L.node_stride * 2u;
     mbar_init(bar, 1);
     mbar_init(bar2, 1);
-    mbar_expect_tx(bar, sbytes);
-    bulk_g2s(succ, a.ws.msucc + b * L.node_stride, sbytes, bar);
     if (a.dur_tma) {
       mbar_expect_tx(bar2, (uint32_t)n1 * 8u);
       bulk_g2s(s.tq, reinterpret_cast<const long long*>(a.duration) + b * n1, (uint32_t)n1 * 8u, bar2);
     }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // everything above may overlap the tail of the ingest kernel
+  if (tid == 0) {
+    if (b == 0) {
+      if (*a.ws.conj_count != (unsigned long long)a.expect_conj) atomicCAS(a.ws.flag, 0, -5);
+      *a.ws.conj_count = 0ull;   // the workspace is handed back zero-filled (see l2s_eval_coo)
+    }
+    const uint32_t sbytes = (uint32_t)L.node_stride * 2u;
+    mbar_expect_tx(bar, sbytes);
+    bulk_g2s(succ, a.ws.msucc + b * L.node_stride, sbytes, bar);
   }
   int bad = 0;
   auto node_word = [&](int i, long long d) -> int {     // node word of node i from its duration d
