@@ -27,6 +27,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// The per-node loops of the step kernel are kept rolled: unrolled by the compiler they grow the kernel by 600
+// instructions, and with 40 warps at 40 different places of a long straight-line kernel the instruction cache is a
+// measured cost (5 % of the stall samples are instruction fetches; 10x10 at 8192 instances: 22.5 -> 20.6 us rolled).
+#define L2S_LOOP _Pragma("unroll 1")
+
 namespace l2s {
 
 constexpr int kDurMax = 4095;
@@ -549,6 +554,7 @@ __device__ __forceinline__ void invalidate_from(const Layout& L, const Inst& s, 
 // the backward half of tq, so the pass must run after the latest start times have been consumed).
 template <bool kMsu>
 __device__ __forceinline__ void link_pass(const Layout& L, const Inst& s, uint32_t msu, int lane, int nthr = 32) {
+  L2S_LOOP
   for (int i = lane; i < L.n; i += nthr) {
     const unsigned w = (unsigned)lds32(s.walk + 4u * i);
     const unsigned wp = i > 0 ? (unsigned)lds32(s.walk + 4u * (i - 1)) : kWRowEnd;

@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
       // count => 8-byte aligned rows): two adjacent nodes per lane, 64-bit shared loads, 64-bit global stores
       const float ch = a.high, rh = a.r_high, cf = a.fea, rf = a.r_fea;
       float2* const xb = reinterpret_cast<float2*>(a.x + (size_t)b * n1 * 3);
+      L2S_LOOP
       for (int p = lane; p < (n1 >> 1); p += 32) {
         float2* const xo2 = xb + 3 * p;
         const unsigned dw = (unsigned)lds32(s.durw + 4u * p);
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(128, 8) step_kernel(const __grid_constant__ St
     uint2* src = reinterpret_cast<uint2*>(a.emc) + (size_t)b * L.e_mc;
     uint2* dst = src + (size_t)a.B * L.e_mc;
     const unsigned below = (1u << lane) - 1u;
+    L2S_LOOP
     for (int v0 = 1; v0 <= n; v0 += 32) {
       const int v = v0 + lane;
       const unsigned sc = v <= n ? (unsigned)lds16(msu + 2u * v) : 0u;
