@@ -57,6 +57,17 @@ class ShardedBatchNorm1d(nn.BatchNorm1d):
         import torch.distributed as dist
         if not (self.training and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1):
             return super().forward(x)
+        if x.is_cuda:
+            # on the GPU: torch's fused SyncBatchNorm function (per-rank statistics kernel, one all-gather of
+            # [mean, invstd, count], fused normalisation; its backward all-reduces the two gradient sums) -- a handful
+            # of launches instead of ~60 small ones per layer, which matters for a launch-bound policy
+            from torch.nn.modules._functions import SyncBatchNorm as _SyncBN
+            group = self.group if self.group is not None else dist.group.WORLD
+            if self.track_running_stats:
+                self.num_batches_tracked.add_(1)
+            m = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
+            return _SyncBN.apply(x.contiguous(), self.weight, self.bias, self.running_mean, self.running_var, self.eps, m,
+                                 group, dist.get_world_size(group))
         xd = x.double()
         stats = torch.cat([xd.sum(0), (xd * xd).sum(0), xd.new_full((1,), float(x.shape[0]))])
         stats = _AllReduceSum.apply(stats, self.group)

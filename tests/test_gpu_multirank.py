@@ -44,6 +44,40 @@ for pol in ("random", "greedy"):
     logs, taken = env.run(pol, 40, seed=5, log_steps=(10, 40), return_actions=True)
     out[pol + "_inc"] = gather_concat(logs.t().contiguous()).cpu().numpy()
     out[pol + "_taken"] = gather_concat(taken).cpu().numpy()
+# (3) sharded BatchNorm on the GPU (torch's fused SyncBatchNorm function underneath): embeddings and all-reduced
+#     gradients of the 2-rank run == the unsharded run, which every rank recomputes locally with plain BatchNorm
+sys.path.insert(0, os.path.join(os.environ["L2S_ROOT"], "tests"))
+from test_sharding_gloo import _policy_state, _slice_state
+from l2s_b200.policy import Actor, shard_batchnorm
+from l2s_b200.sharding import allreduce_mean_gradients
+n_j, n_m, B = 5, 4, 6
+n1, e_pc, e_mc = n_j * n_m + 2, n_j * (n_m + 1), n_m * (n_j - 1)
+st = tuple(t.to(dev) for t in _policy_state(B, n_j, n_m, seed=4))
+torch.manual_seed(7)
+kw = dict(embedding_l=2, policy_l=2, embedding_type='gin+dghan', heads=1, dropout=0.0)
+ref, sharded = Actor(3, 32, **kw).to(dev), Actor(3, 32, **kw).to(dev)
+sharded.load_state_dict(ref.state_dict())
+shard_batchnorm(sharded)
+def loss_of(model, s):
+    h = model.node_features(s[0], s[1], s[2], s[4].shape[0])
+    idx = s[4].long()
+    ha = torch.gather(h, 1, idx[:, :, 0:1].expand(-1, -1, h.shape[-1]))
+    hb = torch.gather(h, 1, idx[:, :, 1:2].expand(-1, -1, h.shape[-1]))
+    return h, -torch.log_softmax((ha * hb).sum(-1), dim=1)[:, 0].mean()
+h_full, loss_full = loss_of(ref, st)
+loss_full.backward()
+blo, bhi = rank * B // world, (rank + 1) * B // world
+h_loc, loss_loc = loss_of(sharded, _slice_state(st, blo, bhi, n1, e_pc, e_mc))
+loss_loc.backward()
+allreduce_mean_gradients(list(sharded.parameters()))
+gmax = max(float(p.grad.abs().max()) for p in ref.parameters() if p.grad is not None)
+errs = torch.tensor([float((h_loc - h_full[blo:bhi]).detach().abs().max()),
+                     max(float((a.grad - b.grad).abs().max()) / gmax for a, b in zip(sharded.parameters(), ref.parameters())
+                         if b.grad is not None),
+                     max(float((dict(sharded.named_buffers())[k] - v).abs().max()) for k, v in ref.named_buffers()
+                         if v.dtype.is_floating_point)], device=dev)
+dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+out["bn_errs"] = errs.cpu().numpy()
 if rank == 0:
     np.savez(os.environ["L2S_OUT"], **out)
 dist.barrier()
@@ -89,3 +123,5 @@ def test_two_nccl_ranks_equal_one_rank(tmp_path):
         logs, taken = env.run(pol, 40, seed=5, log_steps=(10, 40), return_actions=True)
         assert np.array_equal(got[pol + "_inc"], logs.t().cpu().numpy()), pol
         assert np.array_equal(got[pol + "_taken"], taken.cpu().numpy()), pol
+    err_h, err_g, err_buf = [float(v) for v in got["bn_errs"]]
+    assert err_h < 1e-5 and err_g < 1e-4 and err_buf < 1e-5, (err_h, err_g, err_buf)
