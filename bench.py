@@ -24,6 +24,7 @@ machine edges + reward/incumbent/tabu + critical path + N5 move set for every in
   evaluator : `Evaluator.forward` on the int64 COO edge lists of the same schedules (graphs/s, GB/s).
   large_instances : BASELINE configs[3]: 100x20 and 150x25, 1024 instances sharded over the ranks.
   training : BASELINE configs[4]: n-step REINFORCE on 10x10, 64 rollouts sharded over the ranks, 500-step episode.
+  learned_policy : BASELINE configs[0] / [1] (N = 1): shipped models on syn10x10 x 500 steps and tai20x15 x 5000 steps.
   roofline : algorithmic bytes of one step (SURVEY.md 8d formula) / mean launch duration vs measured HBM peak.
   cpu_baseline : the UNMODIFIED reference `JsspN5.step` (vendored copy in baseline/_ref, oracle/vendor_ref.py) on the
           box's host cores, one process per core on disjoint instance slices, bounded sample.
@@ -494,6 +495,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- phase 4: stateless evaluator (Evaluator.forward drop-in) on the current schedules ----------------
     ms_ev, k_ev = time_evaluator(envs, n_j, n_m, B, K, dev, stream, barrier)
+    ms_ev_strict = time_evaluator_strict(envs, n_j, n_m, B, dev)
 
     # ---- phase 5: fused K-step search (l2s_run): on-device policy, state resident in shared memory ------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -520,6 +522,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- BASELINE configs[3] and configs[4] ------------------------------------------------------------------
     large = None if args.no_large else large_instances(rank, world, dev, lib, sp, stream, barrier)
     training = None if args.no_training else training_episode(rank, world, dev, barrier)
+    learned = learned_policy_rollouts(dev) if (world == 1 and rank == 0 and not args.no_learned) else None
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
     times = torch.tensor([ms_dev / 1e3, t_py, t_capi, ms_ev / 1e3, ms_fused / 1e3, ms_greedy / 1e3, gather_ms / 1e3],
@@ -578,14 +581,18 @@ def run_ours(args, rank, world, local_rank):
                                       "(lazy list[B][P][2] over the pinned records), done)",
                                "steps": k_e2e},
             "evaluator": {"graphs_per_s": world * B * k_ev / t_ev, "ms_per_call": 1e3 * t_ev / k_ev,
-                          "api": "Evaluator.forward(edge_index int64 COO, duration int64, n_j, n_m)",
+                          "api": "Evaluator.forward(edge_index int64 COO, duration int64, n_j, n_m), strict=False (status checked "
+                                 "once after the loop)",
+                          "strict_ms_per_call": ms_ev_strict,
+                          "strict": "default mode: one 4-byte status read-back + sync per call (the reference synchronises "
+                                    "2 x depth times per call), wall clock, rank 0",
                           "algorithmic_bytes_per_graph": bpg, "achieved_gbs": bpg * B * k_ev / t_ev / 1e9,
                           "frac_of_peak": bpg * B * k_ev / t_ev / 1e9 / peak},
             "fused_run": {"random_policy_inst_steps_per_s": world * B * k_f * REPLICAS / t_fused,
                           "greedy_policy_inst_steps_per_s": world * B * k_g / t_greedy,
                           "api": "l2s_run: K steps per launch, on-device policy, no host round trip, no x/edge outputs",
                           "steps_per_launch": k_f},
-            "large_instances": large, "training": training,
+            "large_instances": large, "training": training, "learned_policy": learned,
             "gpu_launches": K1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "l2s::step_kernel",
@@ -626,6 +633,27 @@ def time_evaluator(envs, n_j, n_m, B, K, dev, stream, barrier):
     return ms_ev, k_ev
 
 
+def time_evaluator_strict(envs, n_j, n_m, B, dev):
+    """Default (strict) mode of the drop-in: one status read-back + sync per call, wall clock."""
+    import torch
+    from l2s_b200 import Evaluator
+    n1 = n_j * n_m + 2
+    ev = Evaluator()
+    state, fa, done = envs[0].observe()
+    ei = torch.cat([state[1], state[2]], dim=1).contiguous()
+    dur = torch.zeros((B, n1), dtype=torch.int64, device=dev)
+    dur[:, 1:-1] = torch.from_numpy(envs[0].instances[:, 0].reshape(B, -1).astype(np.int64)).to(dev)
+    dur = dur.reshape(-1, 1)
+    for _ in range(3):
+        ev.forward(ei, dur, n_j, n_m)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ev.forward(ei, dur, n_j, n_m)
+    torch.cuda.synchronize(dev)
+    return 1e3 * (time.perf_counter() - t0) / 20
+
+
 def large_instances(rank, world, dev, lib, sp, stream, barrier):
     """BASELINE configs[3]: synthetic 100x20 and 150x25, batch 1024 sharded over the ranks (1024 / N per GPU)."""
     import torch
@@ -653,6 +681,35 @@ def large_instances(rank, world, dev, lib, sp, stream, barrier):
                       "evaluator_frac_of_peak": bpg * B * k_ev / (ms_ev / 1e3) / 1e9 / peak}
         del rep
         torch.cuda.empty_cache()
+    return out
+
+
+def learned_policy_rollouts(dev):
+    """BASELINE configs[0] / configs[1]: the shipped GIN+DGHAN incumbent models rolled out on syn10x10 (100 instances,
+    500 steps) and tai20x15 (10 instances, 5000 steps) -- the loop of test_learned.py:185-189 with the policy + step pair
+    captured in one CUDA graph (l2s_b200.rollout.GraphedRollout).  Seconds per instance and optimality gaps beside the
+    reference's own stored numbers (unstated GPU)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from rollout_learned import rollout
+    pol = os.path.join(ROOT, "tests", "golden", "policy")
+    out = {}
+    for name, data, weights, steps, ref in (
+            ("syn10x10", "syn10x10", "incumbent_10x10_gin+dghan.pth", 500,
+             {"s_per_instance": {"500": 1.25}, "gap": {"500": 0.0444}}),
+            ("tai20x15", "tai20x15", "incumbent_20x15_gin+dghan.pth", 5000,
+             {"s_per_instance": {"500": 2.93, "5000": 29.45}, "gap": {"500": 0.1163, "1000": 0.1042, "2000": 0.0945, "5000": 0.0831}})):
+        inst = np.load(os.path.join(pol, data + ".npy"))
+        opt = np.load(os.path.join(pol, data + "_result.npy"))
+        rollout(inst, os.path.join(pol, weights), 20, mode="graph")          # warm-up (allocator, capture path)
+        torch.cuda.synchronize(dev)
+        res, secs = rollout(inst, os.path.join(pol, weights), steps, mode="graph")
+        out[name] = {"instances": int(len(inst)), "steps": steps, "seconds": secs, "s_per_instance": secs / len(inst),
+                     "inst_steps_per_s": len(inst) * steps / secs,
+                     "gap": {str(k): float(((v - opt) / opt).mean()) for k, v in sorted(res.items())},
+                     "reference_stored": ref}
+    out["what"] = ("shipped incumbent models, sampling policy (seed 1), policy forward + l2s_step in one CUDA graph per "
+                   "step; the reference's stored s_per_instance include its policy forward on an unstated GPU")
     return out
 
 
@@ -704,6 +761,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large", action="store_true", help="skip the 100x20 / 150x25 section")
     ap.add_argument("--no-training", action="store_true", help="skip the REINFORCE episode")
+    ap.add_argument("--no-learned", action="store_true", help="skip the learned-policy rollouts (configs 0 / 1)")
     ap.add_argument("--no-pin", action="store_true", help="do not bind ranks to their GPU's NUMA-local cores")
     ap.add_argument("--device-only", action="store_true", help="kernel-only timing (skips the e2e phases)")
     args = ap.parse_args()

@@ -116,3 +116,24 @@ def test_cuda_graph_rollout_matches_eager_device_rollout():
     ro.run(40)
     assert env2.itr == 40
     assert torch.equal(env2.current_objs, eager_cur) and torch.equal(env2.incumbent_objs, eager_inc)
+
+
+@pytest.mark.timeout(900)
+def test_tai20x15_5000_step_rollout_matches_reference_statistics():
+    """BASELINE configs[1]: Taillard 20x15 (10 instances), shipped 20x15 gin+dghan incumbent model, 5000 improvement
+    steps, policy + step pair in one CUDA graph.  The reference stores gaps of 11.63 / 10.42 / 9.45 / 8.31 % after
+    500 / 1000 / 2000 / 5000 steps (sampling policy, so this is a statistical check); incumbents never get worse and
+    never beat the best-known upper bounds."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from rollout_learned import rollout
+    inst = np.load(os.path.join(POL, "tai20x15.npy"))
+    best = np.load(os.path.join(POL, "tai20x15_result.npy"))
+    res, secs = rollout(inst, os.path.join(POL, "incumbent_20x15_gin+dghan.pth"), 5000, mode="graph")
+    steps = [500, 1000, 2000, 5000]
+    gaps = [float(((res[k] - best) / best).mean()) for k in steps]
+    for a, b in zip(steps[:-1], steps[1:]):
+        assert (res[b] <= res[a]).all(), "incumbents got worse between %d and %d steps" % (a, b)
+    assert (res[5000] >= best - 1e-6).all()
+    assert 0.08 < gaps[0] < 0.16 and 0.05 < gaps[3] < 0.115, gaps        # reference: 0.1163 ... 0.0831
+    assert gaps[3] < gaps[0] - 0.01
