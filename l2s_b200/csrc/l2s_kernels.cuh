@@ -313,7 +313,7 @@ struct StepArgs {
   uint32_t* rec;
   int rec_stride;          // words per record: 4 + pmax rounded up to a multiple of 16
   int rec_lines;           // write whole 64-byte lines (the words behind 4 + npairs are padding with stale contents)
-  int fast_sweep;          // CTA kernel: latency variant of the wavefront (few resident instances per SM)
+  int fast_sweep;          // CTA kernel: 1 = latency variant of the wavefront (few resident instances per SM), 2 = + look-ahead
   int incremental;         // CTA kernel: resume the sweeps from the cached evaluation st.fq (0: always sweep everything)
   // test introspection (l2s_export_state): evaluate only, no mutation
   int export_only;
@@ -669,20 +669,23 @@ __global__ void __launch_bounds__(256) step_kernel_cta(const __grid_constant__ S
   if (sweep) {
     if (w == 0) {
       int last;
-      const bool ok = a.fast_sweep ? wavefront_fast(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv)
-                                   : wavefront(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv);
+      const bool ok = a.fast_sweep == 2 ? wavefront_fast2(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv)
+                      : a.fast_sweep ? wavefront_fast(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv)
+                                     : wavefront(L, s, lane, 0, lane < L.n_m, last, -1, 0u, startv, prevv);
       const int ms0 = __reduce_max_sync(kFull, last);
       if (lane == 0) { sh[3] = ms0; sh[4] = ok; }
       if (nw == 1) {
         int l2;
-        const bool ok2 = a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2)
-                                      : wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2);
+        const bool ok2 = a.fast_sweep == 2 ? wavefront_fast2(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2)
+                         : a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2)
+                                        : wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, start2, prev2);
         if (lane == 0) sh[5] = ok2;
       }
     } else if (w == 1) {
       int l2;
-      const bool ok2 = a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv)
-                                    : wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv);
+      const bool ok2 = a.fast_sweep == 2 ? wavefront_fast2(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv)
+                       : a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv)
+                                      : wavefront(L, s, lane, 1, lane < L.n_m, l2, -1, 0u, startv, prevv);
       if (lane == 0) sh[5] = ok2;
     }
   } else if (tid == 0) {                   // nothing moved: the cached evaluation stands (fin[T] = makespan)
@@ -1537,12 +1540,14 @@ __global__ void __launch_bounds__(256) coo_eval_kernel_cta(const __grid_constant
   __syncwarp();
   if (w == 0) {
     int last;
-    const bool ok = a.fast_sweep ? wavefront_fast(L, s, lane, 0, lane < n_m, last) : wavefront(L, s, lane, 0, lane < n_m, last);
+    const bool ok = a.fast_sweep == 2 ? wavefront_fast2(L, s, lane, 0, lane < n_m, last)
+                    : a.fast_sweep ? wavefront_fast(L, s, lane, 0, lane < n_m, last) : wavefront(L, s, lane, 0, lane < n_m, last);
     const int ms0 = __reduce_max_sync(kFull, last);
     if (lane == 0) { sh[3] = ms0; sh[4] = ok; }
   } else if (w == 1) {
     int l2;
-    const bool ok2 = a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < n_m, l2) : wavefront(L, s, lane, 1, lane < n_m, l2);
+    const bool ok2 = a.fast_sweep == 2 ? wavefront_fast2(L, s, lane, 1, lane < n_m, l2)
+                     : a.fast_sweep ? wavefront_fast(L, s, lane, 1, lane < n_m, l2) : wavefront(L, s, lane, 1, lane < n_m, l2);
     if (lane == 0) sh[5] = ok2;
   }
   __syncthreads();

@@ -111,14 +111,15 @@ static int run_all(int argc, char** argv, uint64_t* digest) {
   GMALLOC(d_log, sizeof(float) * B);
   GMALLOC(d_flag, sizeof(int32_t));
 
-  for (int variant = 0; variant < 2; ++variant) {   /* 0: defaults, 1: incremental off + flag wait + 64-byte record lines */
+  for (int variant = 0; variant < 2; ++variant) {   /* 0: defaults, 1: flag wait + record lines + action prefetch + look-ahead sweep */
     l2s_handle h;
     CHECK(l2s_create(NJ, NM, B, NJ > 30 ? 128 : 0, 0, &h));
     if (variant == 1) {
-      l2s_set_option(h, "incremental", 0);
+      l2s_set_option(h, "incremental", 1);
       l2s_set_option(h, "host_wait_flag", 1);
       l2s_set_option(h, "host_record_lines", 1);
       l2s_set_option(h, "host_action_prefetch", 1);
+      l2s_set_option(h, "fast_sweep", 2);
     }
     const int pmax = l2s_pmax(h);
     GMALLOC(d_pairs, sizeof(int32_t) * B * pmax * 2);

@@ -350,7 +350,7 @@ def test_evaluator_cta_kernel_matches_reference(cta_warps, monkeypatch):
     from l2s_b200 import Evaluator
     g = np.load(os.path.join(GOLDEN, "eval_coo.npz"))
     monkeypatch.setenv("L2S_EVAL_CTA", cta_warps)
-    for fast in ("0", "1"):
+    for fast in ("0", "1", "2"):
         monkeypatch.setenv("L2S_FAST_SWEEP", fast)
         ev = Evaluator()
         for tag in ("6x4", "10x10", "20x15", "30x20"):

@@ -326,3 +326,31 @@ def test_incremental_step_equals_full_sweep_and_c_oracle(n_j, n_m, B, K, cta, mo
                 s_f, fa_f, _ = full.observe()
                 same("after illegal action")
                 assert np.array_equal(s_i[0].cpu().numpy(), cenv.x)
+
+
+@pytest.mark.parametrize("n_j,n_m,B,cta", [(20, 15, 40, "2"), (12, 7, 30, "1"), (30, 20, 24, "4"), (100, 20, 10, None),
+                                           (9, 32, 12, "8")])
+@pytest.mark.parametrize("fast", ["0", "1", "2"])
+def test_cta_sweep_variants_equal_c_oracle(n_j, n_m, B, cta, fast, monkeypatch):
+    """The three sweep variants of the CTA step kernel (lean, latency, latency + two-operation look-ahead) against the
+    plain-C oracle on a 25-step random trajectory: features, machine edges, est / lst, move sets."""
+    from l2s_b200 import JsspN5
+    from oracle import c_oracle as CO
+    if cta:
+        monkeypatch.setenv("L2S_CTA_WARPS", cta)
+    monkeypatch.setenv("L2S_FAST_SWEEP", fast)
+    inst = gen_instances(n_j, n_m, B, seed=11 * n_j + n_m)
+    env = JsspN5(n_j, n_m, 1, 99)
+    state, fa, done = env.reset(inst, "fdd-divide-mwkr", "cuda")
+    cenv = CO.CEnv(inst, env.solutions().cpu().numpy())
+    rng = np.random.RandomState(int(fast) + 5)
+    for k in range(25):
+        acts = [[int(v) for v in f[rng.randint(len(f))]] for f in fa]
+        state, reward, fa, done = env.step(acts, "cuda")
+        cenv.run("replay", 1, tape=np.array(acts, dtype=np.int32).reshape(B, 1, 2), write_state=True)
+        assert np.array_equal(state[0].cpu().numpy(), cenv.x), k
+        assert np.array_equal(state[2].cpu().numpy(), cenv.emc), k
+        got_np = np.array([0 if f == [[0, 0]] else len(f) for f in fa])
+        assert np.array_equal(got_np, cenv.npairs), k
+    ex = env.export_state()
+    assert np.array_equal(ex["est"].cpu().numpy(), cenv.est) and np.array_equal(ex["lst"].cpu().numpy(), cenv.lst)
