@@ -361,6 +361,35 @@ def timed_device_steps(rep, W, K_total, lib, sp, stream, barrier, dev):
     return ms
 
 
+def timed_device_steps_streams(rep, W, K_total, lib, dev):
+    """The same launches with every replica (an independent environment) on a stream of its own: the tail of one
+    launch overlaps the head of the next.  Aggregate time between a fork event and the join of all streams."""
+    import torch
+    from l2s_b200 import _capi
+    main = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(REPLICAS)]
+    sps = [C.c_void_p(st.cuda_stream) for st in streams]
+    ios = rep.next_ios(W + K_total)
+    for st in streams:
+        st.wait_stream(main)
+    for r, io in ios[:W]:
+        _capi.check(lib.l2s_step(rep.envs[r]._h, C.byref(io), sps[r]), "l2s_step")
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for st in streams:
+        st.wait_event(e0)
+    for r, io in ios[W:]:
+        lib.l2s_step(rep.envs[r]._h, C.byref(io), sps[r])
+    for st in streams:
+        main.wait_stream(st)
+    e1.record(main)
+    torch.cuda.synchronize(dev)
+    st_ = torch.stack([o["status"] for o in rep.outs])
+    assert int(st_.abs().sum()) == 0, "device-side error during the multi-stream region"
+    return e0.elapsed_time(e1)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -383,7 +412,7 @@ def run_ours(args, rank, world, local_rank):
     k_e2e = max(1, args.e2e_steps)                  # python-API steps (~0.5 ms each)
     w_e2e = 3
     K3 = K * max(1, -(-1000 // K))                  # C-ABI e2e steps actually timed
-    T = -(-(W + K1) // REPLICAS) + -(-(w_e2e + k_e2e) // REPLICAS) + -(-(w_e2e + K3) // REPLICAS) + 2
+    T = 2 * (-(-(W + K1) // REPLICAS)) + -(-(w_e2e + k_e2e) // REPLICAS) + -(-(w_e2e + K3) // REPLICAS) + 2
     rep = Replicas(n_j, n_m, B, T, rank, dev)
     envs, tapes, outs = rep.envs, rep.tapes, rep.outs
     stream = torch.cuda.current_stream(dev)
@@ -421,12 +450,15 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
         gather_ms = e0.elapsed_time(e1)
     barrier()
+    ms_streams = timed_device_steps_streams(rep, W, K1, lib, dev)
+    barrier()
     pbar = float(torch.stack([o["npairs"] for o in outs]).float().mean())
     if args.device_only:
         if rank == 0:
             sampler.stop()
             print(json.dumps({"shape": args.shape, "batch": B, "launch_us": 1e3 * ms_dev / K1,
-                              "value": world * B * K1 / (ms_dev / 1e3)}), flush=True)
+                              "value": world * B * K1 / (ms_dev / 1e3),
+                              "streams_us_per_step": 1e3 * ms_streams / K1}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -525,15 +557,15 @@ def run_ours(args, rank, world, local_rank):
     learned = learned_policy_rollouts(dev) if (world == 1 and rank == 0 and not args.no_learned) else None
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
-    times = torch.tensor([ms_dev / 1e3, t_py, t_capi, ms_ev / 1e3, ms_fused / 1e3, ms_greedy / 1e3, gather_ms / 1e3],
-                         dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_dev / 1e3, t_py, t_capi, ms_ev / 1e3, ms_fused / 1e3, ms_greedy / 1e3, gather_ms / 1e3,
+                          ms_streams / 1e3], dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
         allt = [torch.zeros_like(times) for _ in range(world)]
         dist.all_gather(allt, times)
         per_rank = torch.stack(allt).cpu().numpy()
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_py, t_capi, t_ev, t_fused, t_greedy, t_gather = [float(v) for v in times.cpu()]
+    t_dev, t_py, t_capi, t_ev, t_fused, t_greedy, t_gather, t_streams = [float(v) for v in times.cpu()]
     value = world * B * K1 / t_dev
     e2e_py = world * B * k_e2e / t_py
     e2e_capi = world * B * K3 / t_capi
@@ -592,6 +624,11 @@ def run_ours(args, rank, world, local_rank):
                           "greedy_policy_inst_steps_per_s": world * B * k_g / t_greedy,
                           "api": "l2s_run: K steps per launch, on-device policy, no host round trip, no x/edge outputs",
                           "steps_per_launch": k_f},
+            "independent_streams": {"value": world * B * K1 / t_streams, "unit": UNIT, "us_per_step": 1e6 * t_streams / K1,
+                                    "what": "NOT the headline: the same %d launches with each of the %d independent environments "
+                                            "on a CUDA stream of its own, so that the ramp-down of one launch overlaps the "
+                                            "start-up of the next; shows the steady-state rate of the kernel (a single "
+                                            "environment cannot do this: its next step depends on this one)" % (K1, REPLICAS)},
             "large_instances": large, "training": training, "learned_policy": learned,
             "gpu_launches": K1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
