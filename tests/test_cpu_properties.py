@@ -119,3 +119,80 @@ def test_move_lists_behave_like_the_reference_nested_lists():
     assert [lazy._row(b) for b in range(B)] == want       # pure-Python route == C glue route
     if _capi.pylists() is not None:
         assert lazy.tolist() == want
+
+
+def test_n5_bit_logic_equals_reference_case_analysis():
+    """The kernels enumerate N5 moves with `take_i = s_i & ~(s_(i-1) & s_(i+1))` (s_i: path operations i, i+1 share a
+    machine; sentinels s_-1 = s_rg = 1).  Exhaustive check over all machine-label sequences of length 2..9 over 3
+    labels against the reference's case analysis (JsspN5._get_pairs, env/environment.py:84-105, restated in the oracle),
+    including the IndexError corner (two operations on one machine)."""
+    import itertools
+    from oracle import l2s_oracle as O
+
+    def formula(cb):
+        rg = len(cb) - 1
+        s = [1] + [1 if cb[i] == cb[i + 1] else 0 for i in range(rg)] + [1]
+        return [i for i in range(rg) if s[i + 1] and not (s[i] and s[i + 2])]
+
+    def reference(cb):
+        out, rg = [], len(cb) - 1
+        for i in range(rg):
+            if cb[i] == cb[i + 1]:
+                if i == 0:
+                    if cb[i + 1] != cb[i + 2]:
+                        out.append(i)
+                elif cb[i] != cb[i - 1]:
+                    out.append(i)
+                elif i + 1 == rg:
+                    pass
+                elif cb[i + 1] != cb[i + 2]:
+                    out.append(i)
+        return out
+
+    checked = 0
+    for n in range(2, 10):
+        for cb in itertools.product(range(3), repeat=n):
+            try:
+                want = reference(cb)
+            except IndexError:
+                assert n == 2 and cb[0] == cb[1]
+                continue
+            assert formula(cb) == want, cb
+            checked += 1
+    assert checked > 25000
+    # and the oracle's own pair enumeration agrees with the formula on a path with real node ids
+    path, mch = [5, 9, 2, 7, 11, 3], [1, 1, 1, 2, 2, 1]
+    pairs = O.get_pairs(path, mch, None) if hasattr(O, "get_pairs") else None
+    if pairs is not None:
+        assert [[int(a), int(b)] for a, b in pairs] == [[path[i], path[i + 1]] for i in formula(mch)]
+
+
+def test_vendored_reference_is_importable_on_its_own(tmp_path):
+    """`baseline/_ref` (oracle/vendor_ref.py) is what the GPU box has instead of /root/reference: a fresh interpreter
+    pointed at it alone must import the reference (on the repo's torch_geometric drop-in), reset, step and run the
+    reference Actor with the shipped weights."""
+    from oracle import vendor_ref
+    if vendor_ref.vendor() is None:
+        pytest.skip("no reference tree and no vendored copy")
+    code = r'''
+import os, sys
+sys.path.insert(0, os.environ["L2S_ROOT"])
+import numpy as np, torch
+from oracle import ref_harness as H
+assert H.REFERENCE_ROOT == os.environ["L2S_REFERENCE_ROOT"], H.REFERENCE_ROOT
+R = H.load()
+inst = np.load(os.path.join(R.root, "test_data", "syn10x10.npy"))[:3]
+np.random.seed(1)
+env = R.JsspN5(10, 10, 1, 99)
+state, fa, done = env.reset(inst, "fdd-divide-mwkr", "cpu")
+pol = R.Actor(3, 128, embedding_l=4, policy_l=4, embedding_type="gin+dghan", heads=1, dropout=0.0)
+pol.load_state_dict(torch.load(os.path.join(R.root, "saved_model", "incumbent_10x10[1,99]_fdd-divide-mwkr_yaoxin_1_128_4_4_gin+dghan_1_0.0_5e-05_10_500_64_128000_10.pth"), map_location="cpu"))
+bg = R.BatchGraph(); bg.wrapper(*state)
+acts, lp = pol(bg, fa)
+state, r, fa, done = env.step(acts, "cpu")
+res, _ = R.Greedy_baselines(inst[:1], 3, [3], "cpu")
+print("OK", env.itr, float(env.current_objs.sum()), np.asarray(res).shape)
+'''
+    env = dict(os.environ, L2S_ROOT=ROOT, L2S_REFERENCE_ROOT=vendor_ref.DST)
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "OK 1" in res.stdout, res.stderr[-2000:]
