@@ -110,6 +110,8 @@ def run_parity(R, ref, ours, env_reset, env_step, steps, greedy, seed=0):
 @pytest.mark.parametrize("shape,data,B,steps", [("10x10", "syn10x10", 6, 40), ("20x15", "tai20x15", 3, 12)])
 @pytest.mark.parametrize("greedy", [False, True])
 def test_reference_actor_logits_equal_ours_on_reference_env(shape, data, B, steps, greedy):
+    if greedy:
+        steps = 100          # identical greedy trajectories over 100 steps on syn10x10 and tai20x15
     R = ref_harness.load()
     n_j, n_m = [int(v) for v in shape.split("x")]
     inst = np.load(os.path.join(R.root, "test_data", data + ".npy"))[:B]
