@@ -713,7 +713,7 @@ __device__ __forceinline__ bool is_job_first(const Layout& L, int v) {
   const unsigned x = (unsigned)(v - 1);
   unsigned qd = __umulhi(x, L.magic_nm);
   qd -= (qd * (unsigned)L.n_m > x) ? 1u : 0u;
-  return x == qd * (unsigned)L.n_m;
+  return (x == qd * (unsigned)L.n_m) | (L.n_m == 1);   // (the 32-bit magic number does not exist for n_m = 1)
 }
 
 // Swap the adjacent machine pair a0 -> a1 (JsspN5.change_nxgraph_topology, env/environment.py:318-354) in the

@@ -1147,7 +1147,7 @@ __device__ __forceinline__ int coo_edge(const CooIngestArgs& a, long long u64, l
   const bool uop = (ul - 1u) < n, vop = (vl - 1u) < n;
   const bool consec = vl == ul + 1u;
   const unsigned x = ul == 0u ? vl - 1u : ul;                                // S -> v: is v first?   u -> .: is u last?
-  const bool divis = x == __umulhi(x, a.magic_nm) * n_m;                     // exact for x < 2^16
+  const bool divis = (x == __umulhi(x, a.magic_nm) * n_m) | (n_m == 1u);     // exact for x < 2^16; no 32-bit magic for n_m = 1
   const bool machine = uop & vop & !(consec & !divis);
   const bool conj = ((ul == 0u) & vop & divis) | (uop & (vl == n + 1u) & divis) | (uop & vop & consec & !divis);
   if (inrange & machine) a.ws.msucc[bu * (unsigned)a.node_stride + ul] = (uint16_t)vl;

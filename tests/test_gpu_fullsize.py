@@ -119,7 +119,7 @@ def test_input_validation_errors():
         JsspN5(40, 40, 1, 99).reset(gen_instances(40, 40, 1, 1), "spt", "cuda")      # n_m > 32 unsupported
 
 
-@pytest.mark.parametrize("n_j,n_m,B", [(20, 15, 4096), (10, 10, 300), (16, 16, 64), (100, 20, 32), (150, 25, 16), (7, 32, 40)])
+@pytest.mark.parametrize("n_j,n_m,B", [(20, 15, 4096), (10, 10, 300), (16, 16, 64), (100, 20, 32), (150, 25, 16), (7, 32, 40), (4, 1, 50)])
 def test_evaluator_coo_full_size(n_j, n_m, B):
     """Evaluator.forward on shuffled int64 COO == the integer est/lst of the environment (itself checked against
     the oracle above) for the same schedules; malformed inputs are rejected."""
@@ -354,3 +354,62 @@ def test_cta_sweep_variants_equal_c_oracle(n_j, n_m, B, cta, fast, monkeypatch):
         assert np.array_equal(got_np, cenv.npairs), k
     ex = env.export_state()
     assert np.array_equal(ex["est"].cpu().numpy(), cenv.est) and np.array_equal(ex["lst"].cpu().numpy(), cenv.lst)
+
+
+@pytest.mark.parametrize("n_j,n_m,B", [(20, 15, 700), (10, 10, 257), (6, 6, 33), (30, 20, 70), (5, 32, 40), (3, 1, 9)])
+def test_evaluator_edge_orders_and_malformed_lists(n_j, n_m, B):
+    """The reference hands Evaluator.forward cat([edge_index_pc, edge_index_mc]) (env/environment.py:308); the kernels
+    accept any column order.  The environment's own order, block-wise rearrangements and a full shuffle give identical
+    outputs; lists that are not a batch of complete selections are rejected, and the evaluator stays usable."""
+    from l2s_b200 import Evaluator, JsspN5, L2SError
+    inst = gen_instances(n_j, n_m, B, seed=5 * n_j + n_m)
+    env = JsspN5(n_j, n_m, 1, 99)
+    env.reset(inst, "fdd-divide-mwkr", "cuda")
+    env.run("random", 9, seed=2)
+    state, fa, done = env.observe()
+    ex = env.export_state()
+    n1 = n_j * n_m + 2
+    pc, mc = state[1], state[2]
+    E_pc, E_mc = pc.shape[1] // B, mc.shape[1] // B
+    ei = torch.cat([pc, mc], dim=1)
+    dur = torch.zeros((B, n1), dtype=torch.int64, device="cuda")
+    dur[:, 1:-1] = torch.from_numpy(inst[:, 0].reshape(B, -1).astype(np.int64)).cuda()
+    dur = dur.reshape(-1, 1)
+
+    def same(out):
+        est, lst, ms = out
+        return (torch.equal(est.reshape(B, n1), ex["est"].float()) and torch.equal(lst.reshape(B, n1), ex["lst"].float())
+                and torch.equal(ms, env.current_objs))
+
+    ev = Evaluator()
+    for dt in (torch.int64, torch.int32):
+        assert same(ev.forward(ei, dur.to(dt), n_j, n_m))
+    g = B // 2
+    variants = {}
+    v = ei.clone()                                   # one graph's machine block reversed
+    v[:, B * E_pc + g * E_mc: B * E_pc + (g + 1) * E_mc] = torch.flip(mc[:, g * E_mc:(g + 1) * E_mc], dims=[1])
+    variants["descending"] = v
+    v = ei.clone()                                   # two conjunctive columns of one graph exchanged
+    v[:, [g * E_pc, g * E_pc + 1]] = v[:, [g * E_pc + 1, g * E_pc]]
+    variants["pc-swapped"] = v
+    v = ei.clone()                                   # the machine blocks of two graphs exchanged
+    a, b = B * E_pc, B * E_pc + (B - 1) * E_mc
+    v[:, a:a + E_mc], v[:, b:b + E_mc] = ei[:, b:b + E_mc], ei[:, a:a + E_mc]
+    variants["blocks-exchanged"] = v
+    variants["mc-first"] = torch.cat([mc, pc], dim=1)
+    variants["shuffled"] = ei[:, torch.randperm(ei.shape[1], device="cuda")]
+    for name, v in variants.items():
+        assert same(ev.forward(v, dur, n_j, n_m)), name
+    bad = {}
+    v = ei.clone(); v[:, -1] = v[:, -2]; bad["duplicate arc"] = v
+    v = ei.clone(); v[1, B * E_pc + g * E_mc] = v[0, B * E_pc + g * E_mc]; bad["self loop"] = v
+    v = ei.clone(); v[1, B * E_pc + g * E_mc] = g * n1; bad["arc into S"] = v
+    v = ei.clone(); v[0, B * E_pc] = n1 + 1; bad["source in another graph"] = v
+    for name, v in bad.items():
+        with pytest.raises(L2SError):
+            ev.forward(v, dur, n_j, n_m)
+        assert same(ev.forward(ei, dur, n_j, n_m)), name                           # and the workspace is usable again
+    ev = Evaluator(strict=False)
+    out = ev.forward(variants["shuffled"], dur, n_j, n_m)
+    ev.check()
+    assert same(out)
