@@ -12,14 +12,20 @@ A "step" is ONE `l2s_step` launch over one batch: swap + re-evaluation (est, lst
 machine edges + reward/incumbent/tabu + critical path + N5 move set for every instance of the batch.
 
   value : device-resident throughput (state and action tape already in HBM), CUDA events, max over ranks.  The
+          batch is stepped as 4 independent environments of `--batch` instances (they also make the per-step working
+          set exceed the L2), round-robin, each on a CUDA stream of its own: a step of one environment waits for that
+          environment's previous step, while the ramp-down of one launch overlaps the start-up of the next.  The
           timed region is `reps` back-to-back windows of exactly K steps (reps = ceil(1600 / K), so that the region
-          lasts >= ~50 ms whatever K is: a 20-step window is 0.7 ms, far too short next to rank skew and clock
+          lasts >= ~40 ms whatever K is: a 20-step window is 0.5 ms, far too short next to rank skew and clock
           sampling); `steps_timed` = K * reps, `ms_per_step` = region / steps_timed.  No collective inside; the one
           collective of a search -- the final all-gather of makespans and incumbents -- is warmed up and then timed
-          on its own (`final_gather_ms`).
-  e2e   : the same steps through the C-ABI `l2s_step_host` with HOST buffers: the kernel reads the host actions
-          over PCIe from pinned memory and writes one result record per instance (move set, reward, makespan,
-          incumbent, done, status) over PCIe into pinned host memory; the call returns when the records are there.
+          on its own (`final_gather_ms`).  `single_stream` holds the same launches serialised on ONE stream (one
+          launch timed alone; the `roofline` object is computed from it, `roofline.steady_state` from the headline).
+  e2e   : the same steps through the C-ABI with HOST buffers: the kernel reads the host actions over PCIe from pinned
+          memory and writes one result record per instance (move set, reward, makespan, incumbent, done, status) over
+          PCIe into pinned host memory.  One host thread drives the 4 environments through `l2s_step_host_begin` /
+          `l2s_step_host_wait` with 3 of them in flight; every step's records are in host memory and read before that
+          environment's next step is issued.  `e2e.blocking`: one blocking `l2s_step_host` call per step.
   e2e_python_api : the same through the drop-in `JsspN5.step(actions, device)` (Python lists in and out).
   evaluator : `Evaluator.forward` on the int64 COO edge lists of the same schedules (graphs/s, GB/s).
   large_instances : BASELINE configs[3]: 100x20 and 150x25, 1024 instances sharded over the ranks.
@@ -32,6 +38,7 @@ machine edges + reward/incumbent/tabu + critical path + N5 move set for every in
 `--impl reference` times that same unmodified reference path and prints the same JSON line with "impl": "reference".
 """
 import argparse
+import collections
 import ctypes as C
 import json
 import os
@@ -47,6 +54,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "N5 LS steps/sec (instances x steps)"
 UNIT = "inst-steps/s"
+PIPE_DEPTH = 3     # independent environments in flight in the pipelined e2e loop (< REPLICAS)
 REPLICAS = 4        # rotating independent batches so that the per-step working set exceeds the 126 MB L2
 MIN_TIMED_STEPS = 1600
 
@@ -412,7 +420,7 @@ def run_ours(args, rank, world, local_rank):
     k_e2e = max(1, args.e2e_steps)                  # python-API steps (~0.5 ms each)
     w_e2e = 3
     K3 = K * max(1, -(-1000 // K))                  # C-ABI e2e steps actually timed
-    T = 2 * (-(-(W + K1) // REPLICAS)) + -(-(w_e2e + k_e2e) // REPLICAS) + -(-(w_e2e + K3) // REPLICAS) + 2
+    T = 2 * (-(-(W + K1) // REPLICAS)) + -(-(w_e2e + k_e2e) // REPLICAS) + 2 * (-(-(w_e2e + K3) // REPLICAS)) + 2
     rep = Replicas(n_j, n_m, B, T, rank, dev)
     envs, tapes, outs = rep.envs, rep.tapes, rep.outs
     stream = torch.cuda.current_stream(dev)
@@ -490,7 +498,7 @@ def run_ours(args, rank, world, local_rank):
     pinned_tapes = [t.numpy() for t in pinned_keep]
     hb = []
     p3 = list(pos)
-    for k in range(w_e2e + K3):
+    for k in range(2 * (w_e2e + K3)):
         r = k % REPLICAS
         hb.append((r, pinned_tapes[r][p3[r]]))
         p3[r] += 1
@@ -519,10 +527,48 @@ def run_ours(args, rank, world, local_rank):
         capi_step(r, ptr)
     barrier()
     t0 = time.perf_counter()
-    for r, ptr in calls[w_e2e:]:
+    for r, ptr in calls[w_e2e:w_e2e + K3]:
         capi_step(r, ptr)
     torch.cuda.synchronize(dev)
     t_capi = time.perf_counter() - t0
+    assert not any((e._h_rec[:, 0] >> 24).any() for e in envs)
+
+    # the same steps with the call split in two (l2s_step_host_begin / l2s_step_host_wait): the host thread keeps
+    # PIPE_DEPTH of the REPLICAS independent environments in flight, so the launch + completion latency of one step
+    # hides behind the kernels of the others; every step still takes its actions from host memory and its records are
+    # in host memory (and touched) before that environment's next step is issued
+    begin, wait = lib.l2s_step_host_begin, lib.l2s_step_host_wait
+    own_streams = [torch.cuda.Stream(device=dev) for _ in range(REPLICAS)]
+    for st in own_streams:
+        st.wait_stream(stream)
+    sps_own = [C.c_void_p(st.cuda_stream) for st in own_streams]
+
+    def finish(r):
+        st = wait(handles[r], None, None, None, None, None, None)
+        if st < 0:
+            _capi.check(st, "l2s_step_host_wait")
+        rec = recs[r]
+        return int(rec[0, 0]) + int(rec[-1, 0])
+
+    def pipelined(seq):
+        inflight = collections.deque()
+        for r, ptr in seq:
+            if len(inflight) == PIPE_DEPTH:
+                finish(inflight.popleft())
+            st = begin(handles[r], io_refs[r], ptr, sps_own[r])
+            if st < 0:
+                _capi.check(st, "l2s_step_host_begin")
+            inflight.append(r)
+        while inflight:
+            finish(inflight.popleft())
+
+    rest = calls[w_e2e + K3:]
+    pipelined(rest[:w_e2e])
+    barrier()
+    t0 = time.perf_counter()
+    pipelined(rest[w_e2e:])
+    torch.cuda.synchronize(dev)
+    t_pipe = time.perf_counter() - t0
     assert not any((e._h_rec[:, 0] >> 24).any() for e in envs)
 
     # ---- phase 4: stateless evaluator (Evaluator.forward drop-in) on the current schedules ----------------
@@ -558,15 +604,15 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
     times = torch.tensor([ms_dev / 1e3, t_py, t_capi, ms_ev / 1e3, ms_fused / 1e3, ms_greedy / 1e3, gather_ms / 1e3,
-                          ms_streams / 1e3], dtype=torch.float64, device=dev)
+                          ms_streams / 1e3, t_pipe], dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
         allt = [torch.zeros_like(times) for _ in range(world)]
         dist.all_gather(allt, times)
         per_rank = torch.stack(allt).cpu().numpy()
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_py, t_capi, t_ev, t_fused, t_greedy, t_gather, t_streams = [float(v) for v in times.cpu()]
-    value = world * B * K1 / t_dev
+    t_dev, t_py, t_capi, t_ev, t_fused, t_greedy, t_gather, t_streams, t_pipe = [float(v) for v in times.cpu()]
+    value = world * B * K1 / t_streams              # headline: every independent environment on a stream of its own
     e2e_py = world * B * k_e2e / t_py
     e2e_capi = world * B * K3 / t_capi
 
@@ -588,11 +634,14 @@ def run_ours(args, rank, world, local_rank):
         bpg = bytes_per_graph(n_j, n_m)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "steps_timed": K1, "ms_per_step": 1e3 * t_dev / K1, "higher_is_better": True, "scaling": "weak",
+            "steps_timed": K1, "ms_per_step": 1e3 * t_streams / K1, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": config_of(args, world),
-            "run": {"timed_region": "%d windows of %d steps back to back = %d l2s_step launches between two CUDA events on "
-                                    "the launching stream (%.1f ms); no collective inside" % (reps, K, K1, 1e3 * t_dev),
+            "run": {"timed_region": "%d windows of %d steps back to back = %d l2s_step launches, the %d independent environments "
+                                    "round-robin, each on a CUDA stream of its own (a step of one environment still waits "
+                                    "for that environment's previous step), between a fork event and the join of the "
+                                    "streams (%.1f ms); no collective inside; the same launches on ONE stream: see "
+                                    "single_stream" % (reps, K, K1, REPLICAS, 1e3 * t_streams),
                     "l2": "%d independent batches stepped round-robin: per-step working set x%d > 126 MB L2"
                           % (REPLICAS, REPLICAS),
                     "mean_pairs": pbar, "final_gather_ms": 1e3 * t_gather,
@@ -600,14 +649,23 @@ def run_ours(args, rank, world, local_rank):
                                     "(500 steps in the named config), warmed up, timed on its own" % B,
                     "affinity": affinity,
                     "per_rank_ms": None if per_rank is None else
-                    {"device_steps": [round(1e3 * v, 3) for v in per_rank[:, 0]],
-                     "e2e_capi": [round(1e3 * v, 3) for v in per_rank[:, 2]]}},
-            "e2e": {"value": e2e_capi, "unit": UNIT,
-                    "api": "C-ABI l2s_step_host: host int32 actions in (read in place from pinned memory by the kernel), "
-                           "host records out (pairs/npairs/done/reward/makespan/incumbent/status, written into pinned "
-                           "memory by the kernel), the call returns when the records are in host memory",
+                    {"device_steps": [round(1e3 * v, 3) for v in per_rank[:, 7]],
+                     "device_steps_single_stream": [round(1e3 * v, 3) for v in per_rank[:, 0]],
+                     "e2e": [round(1e3 * v, 3) for v in per_rank[:, 8]],
+                     "e2e_blocking": [round(1e3 * v, 3) for v in per_rank[:, 2]]}},
+            "e2e": {"value": world * B * K3 / t_pipe, "unit": UNIT,
+                    "api": "C-ABI l2s_step_host_begin / l2s_step_host_wait (the two halves of l2s_step_host): host int32 "
+                           "actions in (read in place from pinned memory by the kernel), host records out "
+                           "(pairs/npairs/done/reward/makespan/incumbent/status, written into pinned memory by the kernel); "
+                           "one host thread keeps %d of the %d independent environments in flight, each on its own stream; "
+                           "a step's records are in host memory and read before that environment's next step is issued"
+                           % (PIPE_DEPTH, REPLICAS),
                     "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": int(B * (16 + 4 * pbar)),
-                    "steps": K3, "us_per_step": 1e6 * t_capi / K3},
+                    "steps": K3, "us_per_step": 1e6 * t_pipe / K3, "depth": PIPE_DEPTH,
+                    "blocking": {"value": e2e_capi, "unit": UNIT, "us_per_step": 1e6 * t_capi / K3, "steps": K3,
+                                 "api": "l2s_step_host (one call per step, returns when the records are in host memory; "
+                                        "what the Python drop-in's JsspN5.step uses): launch + completion latency exposed "
+                                        "on every step"}},
             "e2e_python_api": {"value": e2e_py, "unit": UNIT,
                                "api": "drop-in JsspN5.step(actions: list[B][2], device) -> (state, reward, feasible_actions "
                                       "(lazy list[B][P][2] over the pinned records), done)",
@@ -624,16 +682,21 @@ def run_ours(args, rank, world, local_rank):
                           "greedy_policy_inst_steps_per_s": world * B * k_g / t_greedy,
                           "api": "l2s_run: K steps per launch, on-device policy, no host round trip, no x/edge outputs",
                           "steps_per_launch": k_f},
-            "independent_streams": {"value": world * B * K1 / t_streams, "unit": UNIT, "us_per_step": 1e6 * t_streams / K1,
-                                    "what": "NOT the headline: the same %d launches with each of the %d independent environments "
-                                            "on a CUDA stream of its own, so that the ramp-down of one launch overlaps the "
-                                            "start-up of the next; shows the steady-state rate of the kernel (a single "
-                                            "environment cannot do this: its next step depends on this one)" % (K1, REPLICAS)},
+            "single_stream": {"value": world * B * K1 / t_dev, "unit": UNIT, "us_per_step": 1e6 * t_dev / K1,
+                              "what": "the same %d launches back to back on ONE stream (round-1 / early round-2 headline): "
+                                      "launches serialise, so every launch pays its own start-up burst and ramp-down "
+                                      "(9 us + 17.2 us per wave of 5920 instances); the roofline object is computed from "
+                                      "this launch time" % K1},
             "large_instances": large, "training": training, "learned_policy": learned,
             "gpu_launches": K1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "l2s::step_kernel",
-                         "algorithmic_bytes_per_launch": bps * B, "launch_ms": 1e3 * launch_s},
+                         "algorithmic_bytes_per_launch": bps * B, "launch_ms": 1e3 * launch_s,
+                         "launch": "one launch timed alone (single_stream: launches serialised on one stream)",
+                         "steady_state": {"achieved": bps * B * K1 / t_streams / 1e9,
+                                          "frac": bps * B * K1 / t_streams / 1e9 / peak,
+                                          "how": "algorithmic bytes of all timed launches / timed region of the headline "
+                                                 "schedule (launches of independent environments overlap head to tail)"}},
             "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -133,6 +133,17 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
                   int32_t* npairs_host, uint8_t* done_host, float* reward_host, float* makespan_host,
                   int32_t* status_host, void* stream);
 
+/* The same call in two halves, for a host that drives SEVERAL independent environments (handles) from one thread and
+ * wants the launch + completion latency of one hidden behind the kernels of the others: `begin` enqueues the step
+ * (action transfer, kernel, record write-back) on `stream` and returns at once; `wait` blocks until that step's
+ * records are in host memory (an event recorded behind the kernel, so later work on the same stream is not waited
+ * for) and unpacks them like l2s_step_host.  One step in flight per handle (a second `begin` before `wait` is
+ * L2S_ERR_INVALID_ARG); `actions_host` must stay untouched until `wait` returns when the kernel reads it in place.
+ * l2s_step_host(...) == begin(...) followed by wait(...). */
+int l2s_step_host_begin(l2s_handle h, const l2s_step_io* io, const int32_t* actions_host, void* stream);
+int l2s_step_host_wait(l2s_handle h, int32_t* pairs_host, int32_t* npairs_host, uint8_t* done_host, float* reward_host,
+                       float* makespan_host, int32_t* status_host);
+
 /* Host result records of l2s_step_host: `records` is [batch][stride_words] uint32 in pinned host memory owned by
  * the handle, stride_words = L2S_REC_HEADER_WORDS + pmax rounded up to a multiple of 16 (every record starts on a
  * 64-byte line).  Record of instance b:

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "l2s_step": (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p]),
     "l2s_step_host": (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "l2s_step_host_begin": (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p, C.c_void_p]),
+    "l2s_step_host_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "l2s_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "l2s_host_records": (C.c_int, [C.c_void_p, C.POINTER(c_u32p), c_i32p, C.POINTER(c_i32p)]),
     "l2s_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, c_i32p, C.c_int,

@@ -165,6 +165,10 @@ struct l2s_handle_s {
   uint32_t* h_flag;            // pinned + mapped
   uint32_t* h_flag_dev;
   uint32_t flag_epoch;
+  // l2s_step_host_begin .. l2s_step_host_wait
+  cudaEvent_t ev_done;
+  int pending;                 // a begun step has not been waited for yet
+  cudaStream_t pending_stream;
 };
 
 // cuStreamWriteValue32 through the runtime's driver entry-point lookup (no link-time dependency on libcuda)
@@ -357,6 +361,8 @@ static int create_into(l2s_handle h, int n_j, int n_m, int batch, int pmax, int 
   memset(h->h_flag, 0, 64);
   CU(cudaHostGetDevicePointer((void**)&h->h_flag_dev, h->h_flag, 0));
   h->flag_epoch = 0;
+  CU(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  h->pending = 0;
   h->wait_flag = 0;
   h->host_debug = 0;
   h->rec_lines = 0;
@@ -397,6 +403,7 @@ int l2s_destroy(l2s_handle h) {
   cudaFree(h->st.fq); cudaFree(h->st.evalid);
   cudaFree(h->d_rec); cudaFreeHost(h->h_rec); cudaFree(h->d_actions); cudaFreeHost(h->h_actions);
   cudaFreeHost(h->h_flag);
+  cudaEventDestroy(h->ev_done);
   free(h);
   return L2S_OK;
 }
@@ -542,7 +549,14 @@ int l2s_host_records(l2s_handle h, const uint32_t** records, int* stride_words, 
 int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_host, int32_t* pairs_host,
                   int32_t* npairs_host, uint8_t* done_host, float* reward_host, float* makespan_host,
                   int32_t* status_host, void* stream) {
+  const int r = l2s_step_host_begin(h, io, actions_host, stream);
+  if (r != L2S_OK) return r;
+  return l2s_step_host_wait(h, pairs_host, npairs_host, done_host, reward_host, makespan_host, status_host);
+}
+
+int l2s_step_host_begin(l2s_handle h, const l2s_step_io* io, const int32_t* actions_host, void* stream) {
   if (!h || !io) return L2S_ERR_INVALID_ARG;
+  if (h->pending) return L2S_ERR_INVALID_ARG;   // one step in flight per handle: wait for it first
   if (io->reward_type != L2S_REWARD_YAOXIN && io->reward_type != L2S_REWARD_CONSECUTIVE) return L2S_ERR_INVALID_ARG;
   CU(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -591,8 +605,24 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
   if (!io->is_reset && a.actions) h->itr += 1;
   if (!h->rec_direct) CU(cudaMemcpyAsync(h->h_rec, h->d_rec, h->rec_bytes, cudaMemcpyDeviceToHost, s));
   if (h->wait_flag) {
-    const uint32_t epoch = ++h->flag_epoch;
-    if (resolve_write32()(s, (unsigned long long)(uintptr_t)h->h_flag_dev, epoch, 0u) != 0) return L2S_ERR_CUDA;
+    if (resolve_write32()(s, (unsigned long long)(uintptr_t)h->h_flag_dev, ++h->flag_epoch, 0u) != 0) return L2S_ERR_CUDA;
+  } else {
+    CU(cudaEventRecord(h->ev_done, s));
+  }
+  h->pending = 1;
+  h->pending_stream = s;
+  return L2S_OK;
+}
+
+int l2s_step_host_wait(l2s_handle h, int32_t* pairs_host, int32_t* npairs_host, uint8_t* done_host, float* reward_host,
+                       float* makespan_host, int32_t* status_host) {
+  if (!h || !h->pending) return L2S_ERR_INVALID_ARG;
+  CU(cudaSetDevice(h->device));
+  const size_t B = h->B;
+  cudaStream_t s = h->pending_stream;
+  h->pending = 0;
+  if (h->wait_flag) {
+    const uint32_t epoch = h->flag_epoch;
     volatile uint32_t* flag = h->h_flag;
     for (unsigned long long spins = 1; *flag != epoch; ++spins) {
 #if defined(__x86_64__)
@@ -607,10 +637,10 @@ int l2s_step_host(l2s_handle h, const l2s_step_io* io, const int32_t* actions_ho
       }
     }
   } else {
-    CU(cudaStreamSynchronize(s));
+    CU(cudaEventSynchronize(h->ev_done));
   }
   if (pairs_host || npairs_host || status_host || reward_host || makespan_host || done_host) {
-    const size_t stride = (size_t)a.rec_stride;
+    const size_t stride = (size_t)h->rec_stride;
     for (size_t b = 0; b < B; ++b) {   // unpack the records; only the valid prefix of every pair row is defined
       const uint32_t* rec = h->h_rec + b * stride;
       const int np = (int)L2S_REC_NPAIRS(rec[0]);

@@ -320,6 +320,52 @@ def test_step_host_reads_pinned_caller_memory_in_place():
         assert np.array_equal(r0, r1) and np.array_equal(x0, x1)
 
 
+def test_step_host_begin_wait_pipelines_independent_environments():
+    """Two environments driven by one host thread through l2s_step_host_begin / l2s_step_host_wait with both steps in
+    flight on the same stream: every step's records and device outputs equal the golden trajectory (= the blocking
+    call); a second begin before wait, and a wait without begin, are rejected."""
+    import ctypes as C
+    from l2s_b200 import JsspN5, _capi
+    g = np.load(os.path.join(GOLDEN, "traj_10x10.npz"))
+    n_j, n_m, high, fea = [int(v) for v in g["meta"]]
+    lib = _capi.lib()
+    B = g["instances"].shape[0]
+    half = B // 2
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    envs, ios, xs, pins = [], [], [], []
+    for sl in (slice(0, half), slice(half, B)):
+        env = JsspN5(n_j, n_m, 1, high, reward_type=str(g["reward_type"]), fea_norm_const=fea)
+        state, fa, done = env.reset(g["instances"][sl], str(g["init_type"]), "cuda", init_solutions=g["mseq0"][sl])
+        x = torch.empty_like(state[0])
+        emc = torch.empty_like(state[2])
+        nb = len(range(*sl.indices(B)))
+        ms = torch.empty((nb, 1), device="cuda")
+        ios.append(_capi.StepIO(actions=None, high=float(high), fea_norm_const=float(fea),
+                                reward_type=_capi.REWARD[str(g["reward_type"])], is_reset=0, x=x.data_ptr(),
+                                edge_index_mc=emc.data_ptr(), makespan=ms.data_ptr(), incumbent=None, reward=None,
+                                done=None, pairs=None, npairs=None, status=None))
+        envs.append(env)
+        xs.append((x, emc, ms, sl))
+    assert lib.l2s_step_host_wait(envs[0]._h, None, None, None, None, None, None) < 0          # nothing begun
+    for k in range(g["tape"].shape[1]):
+        keep = [torch.from_numpy(np.ascontiguousarray(g["tape"][sl, k]).astype(np.int32)).pin_memory() for *_, sl in xs]
+        for e in (0, 1):
+            _capi.check(lib.l2s_step_host_begin(envs[e]._h, C.byref(ios[e]), keep[e].data_ptr(), sp), "begin")
+        assert lib.l2s_step_host_begin(envs[0]._h, C.byref(ios[0]), keep[0].data_ptr(), sp) < 0   # one in flight per handle
+        for e in (1, 0):                                                          # (waited for out of order)
+            nb = xs[e][2].shape[0]
+            npairs = np.zeros(nb, dtype=np.int32)
+            mk = np.zeros(nb, dtype=np.float32)
+            _capi.check(lib.l2s_step_host_wait(envs[e]._h, None, npairs.ctypes.data, None, None, mk.ctypes.data, None),
+                        "wait")
+            x, emc, ms, sl = xs[e]
+            assert np.array_equal(npairs, g["npairs"][k + 1][sl])
+            assert np.array_equal(mk.astype(np.int32), g["makespan"][k + 1][sl])
+        torch.cuda.synchronize()
+        for x, emc, ms, sl in xs:
+            assert np.array_equal(ms.cpu().numpy().reshape(-1).astype(np.int32), g["makespan"][k + 1][sl])
+
+
 def test_plist_reset_matches_reference_golden():
     """a-14: reset(init_type='plist') under the reference run's numpy seed reproduces its first state, move sets and a
     40-step trajectory (tests/golden/plist_10x5.npz, generated from the unmodified reference)."""
