@@ -147,10 +147,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def pin_to_gpu_numa(local_rank, world):
+def pin_to_gpu_numa(local_rank, world, force=False):
     """Bind this rank to its own share of the cores local to its GPU's NUMA node (the e2e loop is one host thread
     per rank that launches, waits and reads pinned memory: migrations and remote-node memory cost microseconds per
-    step).  Returns a description, or None when the topology cannot be read."""
+    step).  Only when the box has more than one NUMA node (`force` binds anyway: diagnostics).  Returns a description,
+    or None when the topology cannot be read."""
     try:
         import torch
         def cpulist(i):
@@ -169,6 +170,11 @@ def pin_to_gpu_numa(local_rank, world):
         local = [c for c in mine if c in allowed]
         if not local:
             return None
+        if len(local) == len(allowed) and not force:
+            # one NUMA node: every core is local to every GPU, nothing to gain from a binding (measured on this pool's
+            # 8-GPU box, 32 cores, one node: pipelined e2e 26.5 us per step unbound vs 28-35 us with 4 cores per rank;
+            # profiles/e2e_pipeline_ranks_r2.json)
+            return {"numa_cores": len(local), "ranks_on_node": min(world, torch.cuda.device_count()), "bound_to": None}
         n_local = min(world, torch.cuda.device_count())
         sharing = [i for i in range(n_local) if cpulist(i) == mine]
         k, idx = len(sharing), sharing.index(local_rank)
@@ -717,8 +723,11 @@ def time_evaluator(envs, n_j, n_m, B, K, dev, stream, barrier):
         dur[:, 1:-1] = torch.from_numpy(envs[r].instances[:, 0].reshape(B, -1).astype(np.int64)).to(dev)
         ev_in.append((ei, dur.reshape(-1, 1)))
     k_ev = max(24, min(K, 40))
-    for r in range(2 * len(envs)):          # warm-up: every input once, allocator and lazy kernel loading settled
-        ev.forward(ev_in[r % len(envs)][0], ev_in[r % len(envs)][1], n_j, n_m)
+    # warm-up: every input twice, lazy kernel loading settled -- and the outputs BOUND like in the timed loop, so that two
+    # sets of output tensors are alive at a time and the caching allocator has grown to that before the window (with
+    # the results dropped, the first timed call paid a cudaMalloc: 100x20 at 128 graphs read 79-510 us instead of 33)
+    for r in range(2 * len(envs)):
+        est, lst, mk = ev.forward(ev_in[r % len(envs)][0], ev_in[r % len(envs)][1], n_j, n_m)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)

@@ -52,7 +52,7 @@ def main():
     recs = [e._h_rec for e in rep.envs]
     own_streams = [torch.cuda.Stream(dev) for _ in range(bench.REPLICAS)]
     pos = list(rep.pos)
-    bench.pin_to_gpu_numa(0, 1)
+    bench.pin_to_gpu_numa(0, 1, force=True)
     rows = []
     for depth, own, pf, ln in combos:
         for h in handles:

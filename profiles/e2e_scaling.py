@@ -78,7 +78,7 @@ def main():
             for k, v in opts.items():
                 _capi.check(lib.l2s_set_option(h, k.encode(), v), "l2s_set_option")
         os.sched_setaffinity(0, free_affinity)
-        aff = bench.pin_to_gpu_numa(local, world) if "pin" in parts else None
+        aff = bench.pin_to_gpu_numa(local, world, force=True) if "pin" in parts else None
         calls = []
         for k in range(8 + K):
             r = k % bench.REPLICAS
