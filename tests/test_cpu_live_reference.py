@@ -1,0 +1,75 @@
+"""CPU parity of the oracle against the LIVE, unmodified reference (imported from /root/reference or the vendored
+`baseline/_ref`) on shapes the golden fixtures do not hold: single-machine instances (n_m = 1: every operation is the
+first and the last of its job, the machine chain joins consecutive node ids) and very small / very flat shapes.
+The GPU suite checks the CUDA path against the same oracle on these shapes (`test_odd_shapes_against_c_oracle`,
+`test_evaluator_coo_full_size[4-1-50]`, `test_evaluator_edge_orders_and_malformed_lists[3-1-9]`)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import l2s_oracle as O
+from oracle import ref_harness
+
+pytestmark = pytest.mark.skipif(not ref_harness.available(), reason="reference tree / baseline/_ref not present")
+
+
+@pytest.mark.parametrize("n_j,n_m", [(3, 1), (4, 1), (9, 1), (2, 2), (2, 5), (7, 2)])
+def test_reference_evaluator_on_odd_shapes(n_j, n_m):
+    """Evaluator.forward of the reference (env/message_passing_evl.py:161-199) on random ACYCLIC machine orders --
+    for n_m = 1 any permutation of the jobs -- equals the oracle's topological evaluation and its literal Jacobi
+    restatement, node for node."""
+    R = ref_harness.load()
+    rng = np.random.RandomState(11 * n_j + n_m)
+    n, n1, B = n_j * n_m, n_j * n_m + 2, 7
+    eis, durs, want = [], [], []
+    pc = O.edge_index_pc(n_j, n_m)
+    for b in range(B):
+        dur = rng.randint(1, 30, size=(n_j, n_m))
+        mch = rng.random_sample((n_j, n_m)).argsort(axis=1) + 1
+        mseq = O.rules_solver(dur, mch, rule="spt")[0]
+        if n_m == 1:
+            mseq = (rng.permutation(n_j) + 1).reshape(1, n_j)          # any job order is a valid single-machine schedule
+        dur1 = O.padded_durations(dur)
+        mpred, msucc = O.machine_links(mseq, n1)
+        est, lst, ms = O.evaluate(dur1, mpred, msucc, n_j, n_m)
+        want.append((est, lst, ms))
+        eis.append(np.concatenate([pc, O.edge_index_mc(msucc, n)], axis=1) + b * n1)
+        durs.append(dur1)
+    ei = np.concatenate(eis, axis=1)
+    ei = ei[:, rng.permutation(ei.shape[1])]
+    dur = np.concatenate(durs).reshape(-1, 1)
+    r_est, r_lst, r_ms = R.Evaluator().forward(torch.from_numpy(ei), torch.from_numpy(dur), n_j, n_m)
+    j_est, j_lst, j_ms = O.evaluate_coo_jacobi(ei, dur, n_j, n_m)
+    assert np.array_equal(r_est.numpy().reshape(-1), j_est) and np.array_equal(r_lst.numpy().reshape(-1), j_lst)
+    assert np.array_equal(r_ms.numpy().reshape(-1), j_ms)
+    for b, (est, lst, ms) in enumerate(want):
+        assert np.array_equal(r_est.numpy().reshape(B, n1)[b].astype(np.int64), est)
+        assert np.array_equal(r_lst.numpy().reshape(B, n1)[b].astype(np.int64), lst)
+        assert int(r_ms[b]) == ms
+
+
+@pytest.mark.parametrize("n_j", [3, 4, 9])
+def test_reference_single_machine_environment(n_j):
+    """JsspN5 of the reference on single-machine instances with pairwise distinct durations (no priority tie, so `spt`
+    consumes no random number): initial order, features, move sets (always the dummy move: the critical path is one
+    block over the only machine), rewards and incumbents equal the oracle's over a few steps."""
+    R = ref_harness.load()
+    rng = np.random.RandomState(5 * n_j)
+    B = 6
+    dur = np.stack([rng.permutation(n_j) + 1 for _ in range(B)]).reshape(B, n_j, 1)
+    inst = np.stack([dur, np.ones_like(dur)], axis=1).astype(np.int64)
+    env = R.JsspN5(n_j, 1, 1, 99)
+    state, fa, done = env.reset(inst, "spt", "cpu")
+    oenv = O.OracleEnv(n_j, 1, 1, 99)
+    mseq = np.stack([O.rules_solver(i[0], i[1], rule="spt")[0] for i in inst])
+    _, ofa, _ = oenv.reset(inst, mseq=mseq)
+    for k in range(4):
+        x = state[0].numpy().reshape(B, -1, 3)
+        for b, ins in enumerate(oenv.insts):
+            assert np.array_equal(x[b], O.features(ins.dur1, ins.est, ins.lst, 99, 1000)), (k, b)
+            assert [list(p) for p in fa[b]] == [list(p) for p in ofa[b]], (k, b)
+        assert np.array_equal(env.current_objs.numpy().reshape(-1), np.array([i.makespan for i in oenv.insts], np.float32))
+        acts = [list(f[0]) for f in fa]
+        state, rew, fa, done = env.step(acts, "cpu")
+        _, orew, ofa, _ = oenv.step(acts)
+        assert np.array_equal(rew.numpy().reshape(-1), np.asarray(orew, dtype=np.float32).reshape(-1))
