@@ -73,3 +73,41 @@ def test_reference_single_machine_environment(n_j):
         state, rew, fa, done = env.step(acts, "cpu")
         _, orew, ofa, _ = oenv.step(acts)
         assert np.array_equal(rew.numpy().reshape(-1), np.asarray(orew, dtype=np.float32).reshape(-1))
+
+
+@pytest.mark.parametrize("n_j,n_m,steps", [(100, 20, 12), (150, 25, 8)])
+def test_reference_large_instances(n_j, n_m, steps):
+    """BASELINE configs[3] shapes, which no golden fixture holds (the reference needs seconds per instance there): one
+    instance stepped by the live reference, by the numpy oracle and by the C oracle from the reference's own initial
+    machine orders -- features, machine edges, move sets in order, makespan and reward at every step.  (The CUDA path
+    is checked against the C oracle at these shapes in tests/test_gpu_fullsize.py: this closes the chain.)"""
+    from oracle import c_oracle as CO
+    from oracle.make_golden import ref_initial_orders
+    R = ref_harness.load()
+    rng = np.random.RandomState(n_j)
+    dur = rng.randint(1, 99, size=(1, n_j, n_m))
+    mch = rng.random_sample((1, n_j, n_m)).argsort(axis=2) + 1
+    inst = np.stack([dur, mch], axis=1).astype(np.int64)
+    env, state, fa, done, mseq0 = ref_initial_orders(R, inst, "fdd-divide-mwkr", 1)
+    oenv = O.OracleEnv(n_j, n_m, 1, 99)
+    _, ofa, _ = oenv.reset(inst, mseq=mseq0)
+    cenv = CO.CEnv(inst, mseq0, pmax=64)
+    cenv.run("replay", 0, tape=np.zeros((1, 0, 2), np.int32), write_state=True)
+    for k in range(steps + 1):
+        ins = oenv.insts[0]
+        assert np.array_equal(state[0].numpy(), O.features(ins.dur1, ins.est, ins.lst, 99, 1000)), k
+        assert [list(p) for p in fa[0]] == [list(p) for p in ofa[0]], k
+        assert float(env.current_objs[0]) == ins.makespan
+        assert np.array_equal(state[2].numpy(), O.edge_index_mc(ins.msucc, n_j * n_m)), k
+        assert cenv.status == 0 and np.array_equal(cenv.est[0], ins.est) and np.array_equal(cenv.lst[0], ins.lst), k
+        if k:       # (the C oracle writes x / edge_index_mc from its step loop)
+            assert np.array_equal(cenv.x, state[0].numpy()) and np.array_equal(cenv.emc, state[2].numpy()), k
+        assert cenv.pairs[0, :cenv.npairs[0]].tolist() == [list(p) for p in fa[0]], k
+        assert float(cenv.makespan[0]) == ins.makespan and float(cenv.incumbent[0]) == float(env.incumbent_objs[0])
+        if k == steps:
+            break
+        acts = [list(fa[0][rng.randint(len(fa[0]))])]
+        state, rew, fa, done = env.step(acts, "cpu")
+        _, orew, ofa, _ = oenv.step(acts)
+        cenv.run("replay", 1, tape=np.asarray(acts, np.int32).reshape(1, 1, 2), write_state=True)
+        assert float(rew[0]) == float(np.asarray(orew).reshape(-1)[0])
