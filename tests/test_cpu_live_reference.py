@@ -111,3 +111,93 @@ def test_reference_large_instances(n_j, n_m, steps):
         _, orew, ofa, _ = oenv.step(acts)
         cenv.run("replay", 1, tape=np.asarray(acts, np.int32).reshape(1, 1, 2), write_state=True)
         assert float(rew[0]) == float(np.asarray(orew).reshape(-1)[0])
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_reference_differential_on_random_small_shapes(case):
+    """Differential run, live reference vs numpy oracle, on random small shapes (2-9 jobs, 1-6 machines, short
+    durations so that equal-length paths and tabu interplay are frequent), both reward types, random feasible moves
+    mixed with dummy moves: every returned quantity at every step; the reference's IndexError corner
+    (env/environment.py:89-90) must be raised by both or by neither."""
+    from oracle.make_golden import ref_initial_orders
+    R = ref_harness.load()
+    rng = np.random.RandomState(1000 + case)
+    n_j, n_m = int(rng.randint(2, 10)), int(rng.randint(1, 7))
+    B, K = 4, 15
+    high = int(rng.choice([4, 9, 99]))
+    reward_type = "yaoxin" if case % 2 == 0 else "consecutive"
+    init = "spt" if case % 3 == 0 else "fdd-divide-mwkr"
+    dur = rng.randint(1, high, size=(B, n_j, n_m))
+    mch = rng.random_sample((B, n_j, n_m)).argsort(axis=2) + 1
+    inst = np.stack([dur, mch], axis=1).astype(np.int64)
+    n1 = n_j * n_m + 2
+
+    def both(f_ref, f_orc):
+        out = []
+        for f in (f_ref, f_orc):
+            try:
+                out.append(("ok", f()))
+            except IndexError:
+                out.append(("IndexError", None))
+        assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+        return out[0][0] == "ok", out[0][1], out[1][1]
+
+    state_env = {}
+
+    def ref_reset():
+        np.random.seed(case)
+        env = R.JsspN5(n_j, n_m, 1, high, reward_type=reward_type, fea_norm_const=1000)
+        state, fa, done = env.reset(inst, init, "cpu")
+        emc = state[2].numpy()
+        E = emc.shape[1] // B
+        from oracle.make_golden import mseq_from_emc
+        state_env["mseq0"] = np.stack([mseq_from_emc(emc[:, b * E:(b + 1) * E] - b * n1, inst[b, 1], n_j, n_m)
+                                       for b in range(B)]) if E else None
+        return env, state, fa
+
+    try:
+        env, state, fa = ref_reset()
+        ref_err = None
+    except IndexError:
+        ref_err = "IndexError"
+    if state_env.get("mseq0") is None and n_j > 1:
+        # (reset raised before the state existed: take the oracle's own initial orders; only valid without ties)
+        state_env["mseq0"] = np.stack([O.rules_solver(i[0], i[1], rule=init, high=high)[0] for i in inst])
+    oenv = O.OracleEnv(n_j, n_m, 1, high, reward_type=reward_type, fea_norm_const=1000)
+    try:
+        _, ofa, _ = oenv.reset(inst, mseq=state_env["mseq0"])
+        orc_err = None
+    except IndexError:
+        orc_err = "IndexError"
+    if ref_err or orc_err:
+        # with the oracle's own initial orders a tie may have led the two to different schedules: only when the
+        # reference produced its state can the corner be compared
+        if ref_err is None:
+            assert orc_err is None, "oracle raised IndexError on a state the reference accepts"
+        return
+    for k in range(K):
+        x = state[0].numpy().reshape(B, n1, 3)
+        for b, ins in enumerate(oenv.insts):
+            assert np.array_equal(x[b], O.features(ins.dur1, ins.est, ins.lst, high, 1000)), (k, b)
+            assert [list(p) for p in fa[b]] == [list(p) for p in ofa[b]], (k, b, fa[b], ofa[b])
+        assert np.array_equal(env.current_objs.numpy().reshape(-1), np.array([i.makespan for i in oenv.insts], np.float32))
+        acts = [[0, 0] if rng.rand() < 0.15 else list(f[rng.randint(len(f))]) for f in fa]
+        ok, r_out, o_out = both(lambda: env.step(acts, "cpu"), lambda: oenv.step(acts))
+        if not ok:
+            return
+        state, rew, fa, done = r_out
+        _, orew, ofa, odone = o_out
+        assert np.array_equal(rew.numpy().reshape(-1), np.asarray(orew, dtype=np.float32).reshape(-1)), k
+        assert np.array_equal(env.incumbent_objs.numpy().reshape(-1), np.asarray(oenv.incumbent_objs, np.float32).reshape(-1)), k
+
+
+def test_reference_index_error_corner():
+    """Two jobs on one machine: the critical path is two operations of the same machine and `_get_pairs`
+    (env/environment.py:89-90) indexes past its end -- the reference raises IndexError from `reset`; so does the oracle
+    (the CUDA path reports status -9 -> IndexError, tests/test_gpu_fullsize.py::test_odd_shapes_against_c_oracle)."""
+    R = ref_harness.load()
+    inst = np.array([[[[3], [5]], [[1], [1]]]], dtype=np.int64)
+    with pytest.raises(IndexError):
+        R.JsspN5(2, 1, 1, 99).reset(inst, "spt", "cpu")
+    with pytest.raises(IndexError):
+        O.OracleEnv(2, 1, 1, 99).reset(inst, "spt")
