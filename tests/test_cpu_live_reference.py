@@ -175,15 +175,25 @@ def test_reference_differential_on_random_small_shapes(case):
         if ref_err is None:
             assert orc_err is None, "oracle raised IndexError on a state the reference accepts"
         return
+    from oracle import c_oracle as CO
+    cenv = CO.CEnv(inst, state_env["mseq0"], pmax=64, high=float(high))
     for k in range(K):
         x = state[0].numpy().reshape(B, n1, 3)
         for b, ins in enumerate(oenv.insts):
             assert np.array_equal(x[b], O.features(ins.dur1, ins.est, ins.lst, high, 1000)), (k, b)
             assert [list(p) for p in fa[b]] == [list(p) for p in ofa[b]], (k, b, fa[b], ofa[b])
+            # ... and the C oracle (what the full-size GPU tests compare the CUDA path with)
+            assert np.array_equal(cenv.est[b], ins.est) and np.array_equal(cenv.lst[b], ins.lst), (k, b)
+            assert (cenv.pairs[b, :cenv.npairs[b]].tolist() or [[0, 0]]) == [list(p) for p in fa[b]], (k, b)
+        assert cenv.status == 0
         assert np.array_equal(env.current_objs.numpy().reshape(-1), np.array([i.makespan for i in oenv.insts], np.float32))
+        assert np.array_equal(env.current_objs.numpy().reshape(-1), cenv.makespan)
+        assert np.array_equal(env.incumbent_objs.numpy().reshape(-1), cenv.incumbent)
         acts = [[0, 0] if rng.rand() < 0.15 else list(f[rng.randint(len(f))]) for f in fa]
         ok, r_out, o_out = both(lambda: env.step(acts, "cpu"), lambda: oenv.step(acts))
+        cenv.run("replay", 1, tape=np.asarray(acts, np.int32).reshape(B, 1, 2))
         if not ok:
+            assert cenv.status == -9
             return
         state, rew, fa, done = r_out
         _, orew, ofa, odone = o_out
