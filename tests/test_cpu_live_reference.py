@@ -211,3 +211,27 @@ def test_reference_index_error_corner():
         R.JsspN5(2, 1, 1, 99).reset(inst, "spt", "cpu")
     with pytest.raises(IndexError):
         O.OracleEnv(2, 1, 1, 99).reset(inst, "spt")
+
+
+@pytest.mark.parametrize("n_j,n_m", [(6, 4), (8, 3), (5, 5), (10, 2), (4, 6)])
+def test_reference_greedy_baseline_on_random_instances(n_j, n_m):
+    """`Greedy_baselines` of the reference (conventional_baselines_with_long-term-mem.py:154-221: best neighbour by
+    full re-evaluation, first minimum) on random instances == the C oracle's GREEDY policy (the one the fused CUDA
+    policy is checked against), incumbents at every logged step."""
+    import random
+    from oracle import c_oracle as CO
+    from oracle.make_golden import ref_initial_orders
+    R = ref_harness.load()
+    rng = np.random.RandomState(3 * n_j + n_m)
+    B, steps = 5, [1, 2, 5, 10, 20, 40]
+    dur = rng.randint(1, 99, size=(B, n_j, n_m))
+    mch = rng.random_sample((B, n_j, n_m)).argsort(axis=2) + 1
+    inst = np.stack([dur, mch], axis=1).astype(np.int64)
+    _, _, _, _, mseq0 = ref_initial_orders(R, inst, "fdd-divide-mwkr", 1)
+    random.seed(1)
+    np.random.seed(1)
+    res, _ = R.Greedy_baselines(inst, max(steps), list(steps), "cpu")
+    cenv = CO.CEnv(inst, mseq0)
+    _, logs = cenv.run("greedy", max(steps), log_steps=steps)
+    assert cenv.status == 0
+    assert np.array_equal(np.asarray(res, dtype=np.float32).reshape(len(steps), B), logs)
