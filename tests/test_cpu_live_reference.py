@@ -235,3 +235,33 @@ def test_reference_greedy_baseline_on_random_instances(n_j, n_m):
     _, logs = cenv.run("greedy", max(steps), log_steps=steps)
     assert cenv.status == 0
     assert np.array_equal(np.asarray(res, dtype=np.float32).reshape(len(steps), B), logs)
+
+
+@pytest.mark.parametrize("n_j,n_m", [(3, 1), (2, 4), (6, 6), (10, 5), (15, 10), (20, 15)])
+def test_plist_orders_of_the_dropin_equal_the_live_reference(n_j, n_m):
+    """a-14: `reset(..., init_type='plist')` (env/environment.py:140-200, 391-393).  The drop-in builds the machine
+    orders on the host (`JsspN5._plist_orders`, one `np.random.permutation` like the reference) and installs them with
+    `l2s_set_solution`; with the numpy RNG seeded alike, the orders equal those of the live reference's reset (read
+    back from its machine edges) for every instance of the batch -- and the RNG is left in the same state."""
+    from l2s_b200 import JsspN5
+    from oracle.make_golden import mseq_from_emc
+    R = ref_harness.load()
+    rng = np.random.RandomState(17 * n_j + n_m)
+    B = 4
+    dur = rng.randint(1, 99, size=(B, n_j, n_m))
+    mch = rng.random_sample((B, n_j, n_m)).argsort(axis=2) + 1
+    inst = np.stack([dur, mch], axis=1).astype(np.int64)
+    n1 = n_j * n_m + 2
+    np.random.seed(77)
+    try:
+        state, fa, done = R.JsspN5(n_j, n_m, 1, 99).reset(inst, "plist", "cpu")
+    except IndexError:
+        pytest.skip("the reference's own IndexError corner (two-operation critical path on one machine)")
+    after_ref = np.random.randint(1 << 30)
+    emc = state[2].numpy()
+    E = emc.shape[1] // B
+    want = np.stack([mseq_from_emc(emc[:, b * E:(b + 1) * E] - b * n1, inst[b, 1], n_j, n_m) for b in range(B)])
+    np.random.seed(77)
+    got = JsspN5(n_j, n_m, 1, 99)._plist_orders(inst)
+    assert np.random.randint(1 << 30) == after_ref
+    assert np.array_equal(np.asarray(got).reshape(B, n_m, n_j), want)
