@@ -265,3 +265,43 @@ def test_plist_orders_of_the_dropin_equal_the_live_reference(n_j, n_m):
     got = JsspN5(n_j, n_m, 1, 99)._plist_orders(inst)
     assert np.random.randint(1 << 30) == after_ref
     assert np.array_equal(np.asarray(got).reshape(B, n_m, n_j), want)
+
+
+def test_reinforce_loss_equals_the_live_reference_learn():
+    """f-4: `training.reinforce_loss` (vectorised) against the reference's own `RL2S4JSSP.learn`
+    (n-step_reinforce.py:40-61, loaded from the unmodified script): same loss gradient with respect to every
+    log-probability, for random rewards and done patterns (instances that finish part-way included)."""
+    import importlib.util
+    import os
+    import sys
+    import types
+    from l2s_b200.training import reinforce_loss
+    R = ref_harness.load()
+    sys.path.insert(0, R.root)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_nstep_reinforce", os.path.join(R.root, "n-step_reinforce.py"))
+        mod = importlib.util.module_from_spec(spec)
+        saved_argv, sys.argv = sys.argv, [sys.argv[0]]
+        try:
+            spec.loader.exec_module(mod)
+        finally:
+            sys.argv = saved_argv
+    finally:
+        sys.path.remove(R.root)
+    gen = torch.Generator().manual_seed(5)
+    B, n = 7, 10
+    for trial in range(4):
+        rewards = [torch.randint(0, 30, (B, 1), generator=gen).float() for _ in range(n)]
+        first_done = torch.randint(3, n + 4, (B, 1), generator=gen)              # some instances never finish
+        dones = [torch.full((B, 1), t, dtype=torch.long) >= first_done for t in range(n)]
+        base = [torch.randn(B, 1, generator=gen) for _ in range(n)]
+        lp_ref = [b.clone().requires_grad_(True) for b in base]
+        lp_own = [b.clone().requires_grad_(True) for b in base]
+        me = types.SimpleNamespace(eps=np.finfo(np.float32).eps.item())
+        opt = types.SimpleNamespace(zero_grad=lambda: None, step=lambda: None)
+        mod.RL2S4JSSP.learn(me, rewards, lp_ref, dones, opt)
+        reinforce_loss(rewards, lp_own, dones, gamma=float(mod.args.gamma)).backward()
+        for a, b in zip(lp_ref, lp_own):
+            ga = a.grad if a.grad is not None else torch.zeros_like(a)
+            gb = b.grad if b.grad is not None else torch.zeros_like(b)
+            assert torch.allclose(ga, gb, rtol=1e-5, atol=1e-6), trial
