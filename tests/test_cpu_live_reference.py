@@ -305,3 +305,26 @@ def test_reinforce_loss_equals_the_live_reference_learn():
             ga = a.grad if a.grad is not None else torch.zeros_like(a)
             gb = b.grad if b.grad is not None else torch.zeros_like(b)
             assert torch.allclose(ga, gb, rtol=1e-5, atol=1e-6), trial
+
+
+def test_checkpoint_names_follow_the_reference_scheme():
+    """f-4: `training.model_name` built from the reference's OWN default arguments (parameters.py) is the name of the
+    model the reference ships for that configuration (saved_model/, loaded by test_learned.py:141-148)."""
+    import os
+    import sys
+    from l2s_b200.training import model_name
+    R = ref_harness.load()
+    sys.path.insert(0, R.root)
+    try:
+        saved_argv, sys.argv = sys.argv, [sys.argv[0]]
+        try:
+            from parameters import args
+        finally:
+            sys.argv = saved_argv
+    finally:
+        sys.path.remove(R.root)
+    name = model_name('incumbent', args.j, args.m, args.l, args.h, args.init_type, args.reward_type, args.gamma,
+                      args.hidden_dim, args.embedding_layer, args.policy_layer, args.embedding_type, args.heads,
+                      args.drop_out, args.lr, args.steps_learn, args.transit, args.batch_size, args.episodes,
+                      args.step_validation)
+    assert os.path.isfile(os.path.join(R.root, "saved_model", name)), name
