@@ -107,6 +107,13 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export %s" % name
     assert declared == set(_capi.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    # ... and every ctypes prototype has as many arguments as the C declaration
+    code = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    for m in re.finditer(r"\b(l2s_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", code):
+        name, params = m.group(1), m.group(2).strip()
+        n_params = 0 if params in ("", "void") else params.count(",") + 1
+        assert n_params == len(_capi.PROTOTYPES[name][1]), "%s: header %d arguments, ctypes %d" % (
+            name, n_params, len(_capi.PROTOTYPES[name][1]))
     assert _capi.lib().l2s_version() >= 100
     assert _capi.lib().l2s_status_string(-4).decode().startswith("illegal action")
     assert _capi.lib().l2s_eval_coo_workspace_bytes(20, 15, 8) > 0
