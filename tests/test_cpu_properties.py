@@ -196,3 +196,30 @@ print("OK", env.itr, float(env.current_objs.sum()), np.asarray(res).shape)
     env = dict(os.environ, L2S_ROOT=ROOT, L2S_REFERENCE_ROOT=vendor_ref.DST)
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "OK 1" in res.stdout, res.stderr[-2000:]
+
+
+def test_step_io_layout_and_enums_match_the_header(tmp_path):
+    """The ctypes mirror of `l2s_step_io` (l2s_b200/_capi.py) has the C struct's size and field offsets, and the
+    Python-side status / reward / rule / policy codes are the header's enumerators (compiled with gcc from
+    include/l2s_b200.h)."""
+    import ctypes as C
+    from l2s_b200 import _capi
+    fields = [f[0] for f in _capi.StepIO._fields_]
+    enums = (["L2S_ERR_" + k if k != "OK" else "L2S_OK" for k in _capi.STATUS]
+             + ["L2S_REWARD_" + k.upper() for k in _capi.REWARD]
+             + ["L2S_RULE_" + k.upper().replace("-", "_") for k in _capi.RULE]
+             + ["L2S_POLICY_" + k.upper() for k in _capi.POLICY])
+    src = tmp_path / "io.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "l2s_b200.h"\nint main(void) {\n'
+        '  printf("%zu\\n", sizeof(l2s_step_io));\n'
+        + "".join('  printf("%%zu\\n", offsetof(l2s_step_io, %s));\n' % f for f in fields)
+        + "".join('  printf("%%d\\n", (int)%s);\n' % e for e in enums)
+        + "  return 0;\n}\n")
+    exe = tmp_path / "io"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == C.sizeof(_capi.StepIO)
+    assert out[1:1 + len(fields)] == [getattr(_capi.StepIO, f).offset for f in fields]
+    want = list(_capi.STATUS.values()) + list(_capi.REWARD.values()) + list(_capi.RULE.values()) + list(_capi.POLICY.values())
+    assert out[1 + len(fields):] == want
