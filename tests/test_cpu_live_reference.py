@@ -124,10 +124,11 @@ def test_reference_differential_on_random_small_shapes(case):
     rng = np.random.RandomState(1000 + case)
     n_j, n_m = int(rng.randint(2, 10)), int(rng.randint(1, 7))
     B, K = 4, 15
-    high = int(rng.choice([4, 9, 99]))
+    high = 99          # (the reference's left shift uses the global `args.h` = 99 as its "empty slot" sentinel,
+    #                     env/permissible_LS.py:31: any other `high` makes its reset raise IndexError)
     reward_type = "yaoxin" if case % 2 == 0 else "consecutive"
     init = "spt" if case % 3 == 0 else "fdd-divide-mwkr"
-    dur = rng.randint(1, high, size=(B, n_j, n_m))
+    dur = rng.randint(1, int(rng.choice([4, 9, 99])), size=(B, n_j, n_m))
     mch = rng.random_sample((B, n_j, n_m)).argsort(axis=2) + 1
     inst = np.stack([dur, mch], axis=1).astype(np.int64)
     n1 = n_j * n_m + 2
@@ -328,3 +329,38 @@ def test_checkpoint_names_follow_the_reference_scheme():
                       args.drop_out, args.lr, args.steps_learn, args.transit, args.batch_size, args.episodes,
                       args.step_validation)
     assert os.path.isfile(os.path.join(R.root, "saved_model", name)), name
+
+
+@pytest.mark.parametrize("rule", ["spt", "fdd-divide-mwkr"])
+def test_initial_solutions_against_the_live_reference(rule):
+    """a-12 / a-13: `_rules_solver` + `permissibleLeftShift` (env/environment.py:203-289, env/permissible_LS.py) of the
+    live reference on random shapes with tie-heavy and tie-free durations.  The oracle drawing its tie-breaks from an
+    identically seeded RandomState reproduces the reference's machine orders ALWAYS; its first-minimum rule (what the
+    device builder implements, DESIGN.md 4 'known deviations') reproduces them whenever no tie occurred; the C oracle's
+    builder equals the numpy one."""
+    from oracle import c_oracle as CO
+    from oracle.make_golden import mseq_from_emc
+    R = ref_harness.load()
+    ran = with_ties = 0
+    for case in range(60):
+        rng = np.random.RandomState(case)
+        n_j, n_m = int(rng.randint(3, 13)), int(rng.randint(2, 9))
+        high = 99      # (must equal the reference's global args.h, env/permissible_LS.py:31)
+        dur = rng.randint(1, int(rng.choice([3, 6, 99])), size=(1, n_j, n_m))
+        mch = rng.random_sample((1, n_j, n_m)).argsort(axis=2) + 1
+        inst = np.stack([dur, mch], axis=1).astype(np.int64)
+        np.random.seed(case)
+        try:
+            state, fa, done = R.JsspN5(n_j, n_m, 1, high).reset(inst, rule, "cpu")
+        except IndexError:
+            continue                                    # (the reference's two-operation critical path corner)
+        want = mseq_from_emc(state[2].numpy(), inst[0, 1], n_j, n_m)
+        first, ties = O.rules_solver(inst[0, 0], inst[0, 1], rule, high)
+        drawn, _ = O.rules_solver(inst[0, 0], inst[0, 1], rule, high, rng=np.random.RandomState(case))
+        assert np.array_equal(drawn, want), case
+        if ties == 0:
+            assert np.array_equal(first, want), case
+        assert np.array_equal(CO.rules_solver(inst[0, 0], inst[0, 1], rule, high)[0], first), case
+        ran += 1
+        with_ties += ties > 0
+    assert ran >= 30 and with_ties >= 5 and ran - with_ties >= 5, (ran, with_ties)
